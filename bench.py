@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the IK-Lagrangian hot path (BASELINE.json metric: FK+penalty fwd+bwd samples/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one fused forward+backward pass of the hot path over one synthetic batch: per sample the 3-link FK,
+the end-effector error, 3 joint-limit penalties and 12 tip-vs-circle penalties (4 per-sample dynamic obstacles),
+the 16 batch sums, the Lagrangian and d(Lagrangian)/d(theta)  (config 5 of BASELINE.json:
+three_link_arm + cfg_joint_limits_and_4obs_dynamic, batch 2^24 per GPU).  With N > 1 every rank owns its own 2^24
+shard (weak scaling) and each step ends with an NCCL all-reduce of the 16 violation sums so the multiplier update
+sees identical numbers on every rank.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM); `e2e` is the same
+metric through the host-buffer API (pinned host tensors in, gradient + sums back on the host, PCIe copies inside the
+timed region); `roofline` is the fused kernel against the measured HBM copy bandwidth; `cpu_baseline` is the oracle
+port of the reference's PyTorch-eager CPU path timed on this box's host cores.
+
+--impl reference times that CPU path alone (the reference has no GPU-specific code; its arithmetic is PyTorch eager).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "lagrange-dual-learning_b200")
+for p in (ROOT, PKG):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+METRIC = "fk_penalty_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+ALGO_BYTES_PER_SAMPLE = 80          # read theta 12 + target xy 8 + 4x(x,y,r) 48, write dtheta 12
+CONFIG_NAME = "cfg_joint_limits_and_4obs_dynamic"
+GOOD_SLOPE, BAD_SLOPE = 0.005, 1.0   # scripts/experiments/ik_threelink_obs4_dyn.sh:15-16
+
+
+def measured_peak():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  try:
+    with open(path) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  except Exception:
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons while the GPU is busy (B200_PROFILING.md recipe)."""
+  FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.lines = []
+    self.proc = None
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                    "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._pump, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.lines.append((time.time(), line.strip()))
+
+  def stop(self, t0, t1):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, smax, reasons, power = [], [], set(), []
+    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    for ts, line in self.lines:
+      if ts < t0 or ts > t1 + 0.15:
+        continue
+      parts = [x.strip() for x in line.split(",")]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+      except ValueError:
+        continue
+      for n, v in zip(names, parts[3:7]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+            "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_oracle_samples_per_s(batch_log2, steps, warmup):
+  """The reference's CPU path (PyTorch eager fwd + autograd bwd) restated in oracle/ik_oracle.py, all host threads."""
+  import torch
+  from oracle import ik_oracle as O
+  from ikl import synthetic, standard_config
+  torch.set_num_threads(os.cpu_count() or 1)
+  B = 1 << batch_log2
+  ospec = O.spec_from_json(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
+  theta, q_des, obst = synthetic.make_batch(B, seed=0)
+  lam = torch.tensor(synthetic.SHIPPED_LAMBDA_OBS4_DYN)
+  for _ in range(warmup):
+    O.lagrangian_with_grad(theta, q_des, lam, ospec, obst)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    O.lagrangian_with_grad(theta, q_des, lam, ospec, obst)
+  dt = (time.perf_counter() - t0) / steps
+  return B / dt, dt, torch.get_num_threads(), B
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  steps = min(args.steps, 10)
+  warmup = min(max(args.warmup, 1), 3)
+  sps, dt, cores, B = cpu_oracle_samples_per_s(args.cpu_batch_log2, steps, warmup)
+  sample = "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32), batch 2^%d per step, %d steps" % (
+      args.cpu_batch_log2, steps)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+      "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": "three_link_arm + %s, K=16, synthetic theta/target/obstacle batches" % CONFIG_NAME,
+                 "batch_per_step": B, "device": "cpu"},
+      "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+      "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from ikl import ConstraintSpec, standard_config, fused, synthetic, _cabi
+  from ikl.host_pipeline import HostLagrangianPipeline
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise RuntimeError("bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  spec = ConstraintSpec.from_config(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
+  K = spec.num_constraints
+  B = 1 << args.batch_log2
+  lam = list(synthetic.SHIPPED_LAMBDA_OBS4_DYN)
+  theta, q_des, obst = synthetic.make_batch(B, seed=rank, device=str(dev))
+  if args.layout == "planes":
+    th_in, tg_in, ob_in = synthetic.to_planes(theta, q_des, obst)
+  else:
+    th_in, tg_in, ob_in = theta, q_des, obst
+  dtheta = torch.empty_strided(th_in.shape, th_in.stride(), dtype=torch.float32, device=dev)
+  accum = torch.zeros(K, dtype=torch.float64, device=dev)
+  lam_dev = torch.tensor(lam, device=dev)
+
+  def step():
+    viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta)
+    if world > 1:
+      dist.all_reduce(viol)       # 16 floats: every rank sees the global sums that drive the multiplier update
+    return viol, loss
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  launches0 = _cabi.launch_count()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_wall0 = time.time()
+  ev0.record()
+  for _ in range(args.steps):
+    viol, loss = step()
+  ev1.record()
+  barrier()
+  t_wall1 = time.time()
+  launches = _cabi.launch_count() - launches0
+  kernel_name = _cabi.last_kernel_name()
+  ms_total = ev0.elapsed_time(ev1)
+  t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = float(t.item())
+  ms_step = ms_total / args.steps
+  value = world * B / (ms_step * 1e-3)
+
+  # kernel-only duration for the roofline: the same launches back to back with nothing else on the stream
+  kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  n_k = max(args.steps, 20)
+  kev0.record()
+  for _ in range(n_k):
+    fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, dtheta=dtheta)
+  kev1.record()
+  torch.cuda.synchronize()
+  kernel_ms = kev0.elapsed_time(kev1) / n_k
+  # keep the GPU under the same load long enough for nvidia-smi to see it (a 20-step region lasts milliseconds)
+  t_load0 = time.time()
+  while rank == 0 and time.time() - t_load0 < 1.2:
+    for _ in range(200):
+      fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, dtheta=dtheta)
+    torch.cuda.synchronize()
+  t_load1 = time.time()
+  clocks = sampler.stop(t_wall0, t_load1) if sampler else None
+
+  line = None
+  if rank == 0:
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES_PER_SAMPLE * B / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+      try:
+        with open(prof) as f:
+          traffic = json.load(f).get(args.layout, {}).get("dram_bytes_per_launch")
+      except Exception:
+        traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
+                   "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
+                   "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
+                   "parallelism": "batch shard per GPU, all-reduce of 16 violation sums" if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
+                     "peak_source": peak_src},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "native_lib": _cabi.loaded_path(),
+    }
+
+  # ---- end to end through the host-buffer API (rank-local; every rank does the same work) -------------------
+  e2e = None
+  if not args.skip_e2e:
+    del th_in, tg_in, ob_in, dtheta
+    Be = 1 << args.e2e_batch_log2
+    h_theta = theta[:Be].cpu().pin_memory()
+    h_q = q_des[:Be].cpu().pin_memory()
+    h_ob = obst[:Be].cpu().pin_memory()
+    h_dth = torch.empty(Be, 3).pin_memory()
+    del theta, q_des, obst
+    pipe = HostLagrangianPipeline(spec, chunk=1 << args.e2e_chunk_log2, device=dev)
+    for _ in range(2):
+      pipe.run(h_theta, h_q, h_ob, lam, h_dth)
+    barrier()
+    e0 = time.perf_counter()
+    n_e = max(3, min(args.steps, 10))
+    for _ in range(n_e):
+      viol_h, loss_h = pipe.run(h_theta, h_q, h_ob, lam, h_dth)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - e0) / n_e
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e2e = {"value": world * Be / dt, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+           "ms_per_step": dt * 1e3, "batch_per_gpu": Be, "steps": n_e,
+           "api": "ikl.host_pipeline.HostLagrangianPipeline.run (pinned host rows-layout tensors in, host dtheta + sums out)"}
+
+  if rank == 0:
+    line["e2e"] = e2e
+    if not args.skip_cpu:
+      sps, dtc, cores, Bc = cpu_oracle_samples_per_s(args.cpu_batch_log2, 5, 1)
+      line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                              "sample": "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32) on a 2^%d-sample "
+                                        "batch of the same workload, mean of 5 after 1 warm-up (%.0f ms each)" % (args.cpu_batch_log2, dtc * 1e3)}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--warmup", type=int, default=10)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--batch-log2", type=int, default=24)
+  ap.add_argument("--layout", default="planes", choices=["planes", "rows"])
+  ap.add_argument("--e2e-batch-log2", type=int, default=24)
+  ap.add_argument("--e2e-chunk-log2", type=int, default=21)
+  ap.add_argument("--cpu-batch-log2", type=int, default=21)
+  ap.add_argument("--skip-e2e", action="store_true")
+  ap.add_argument("--skip-cpu", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,180 @@
+/*
+ * ikl.h -- C ABI of libikl.so: the B200 (sm_100a) implementation of the inverse-kinematics
+ * Lagrangian hot path of miloknowles/lagrange-dual-learning:
+ *
+ *     batched planar-arm forward kinematics  ->  joint-limit / circular-obstacle penalties
+ *     ->  per-constraint batch sums g[K]  ->  Lagrangian  sum_i lambda_i g_i  and its analytic
+ *     gradient d/d(theta)  ->  dual-ascent multiplier update.
+ *
+ * The reference has no FFI of its own (it is pure Python on PyTorch eager ops); each entry point
+ * below states the reference Python interface it replaces (file:line relative to the reference
+ * repo).  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain C: raw pointers, sizes and element strides.  No torch / C++ types cross this boundary.
+ *   - Every data pointer is a DEVICE pointer valid on `stream` unless the name ends in `_host`.
+ *   - Strides are in ELEMENTS (floats), may be 0 (broadcast) and need not be contiguous; the
+ *     library picks a vectorised kernel when the strides describe one of the two native layouts
+ *     (see IklBatch) and a generic strided kernel otherwise.  Results do not depend on the choice.
+ *   - Ownership: the caller owns every buffer including the workspace.  The library never
+ *     allocates, frees or synchronises; all work is ordered on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).  Calls are re-entrant across streams as long as each
+ *     concurrent call uses its own workspace.
+ *   - Errors: every function returns an IklStatus; nothing throws.  ikl_strerror() names it and
+ *     ikl_last_cuda_error() returns the cudaError_t (as int) behind an IKL_ERR_CUDA on this thread.
+ *   - There is no CPU implementation behind this ABI.  Without a CUDA device every compute entry
+ *     point returns IKL_ERR_CUDA.
+ */
+#ifndef IKL_H_
+#define IKL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IKL_ABI_VERSION 1
+#define IKL_MAX_LINKS 3        /* reference trainer supports 3 (scripts/trainer.py:177-180); 2 is templated too */
+#define IKL_MAX_OBSTACLES 4    /* reference hard-wires (B,4,4): scripts/trainer.py:218, kinematics/dataset.py:80 */
+#define IKL_MAX_CONSTRAINTS (1 + IKL_MAX_LINKS + IKL_MAX_LINKS * IKL_MAX_OBSTACLES)   /* 16 */
+
+typedef enum IklStatus {
+  IKL_OK = 0,
+  IKL_ERR_INVALID_ARGUMENT = 1,   /* null pointer, negative size, K mismatch, negative slope ... */
+  IKL_ERR_UNSUPPORTED = 2,        /* num_links / num_obstacles outside the templated range */
+  IKL_ERR_CUDA = 3                /* a CUDA runtime call failed; see ikl_last_cuda_error() */
+} IklStatus;
+
+/* What a resources/cfg_*.json plus --penalty_good_slope/--penalty_bad_slope reduce to for this path
+ * (scripts/trainer.py:71-99 constraint layout; :170 limits; :203-204, :237 slope assignment;
+ * utils/constants.py:8-10 link lengths). */
+typedef struct IklSpec {
+  int32_t num_links;              /* J: 2 or 3 */
+  int32_t enforce_joint_limits;   /* cfg["enforce_joint_limits"] */
+  int32_t num_obstacles;          /* 0 when cfg["enforce_obstacles"] is false; else 1..4 */
+  int32_t dynamic_obstacles;      /* 1: per-sample obstacles (IklBatch.obstacles); 0: static_obstacles below */
+  float limit_lo, limit_hi;       /* cfg["static_constraints"]["joint_limits"] as float32 */
+  float good_slope, bad_slope;    /* opt.penalty_good_slope / opt.penalty_bad_slope, both >= 0 */
+  float link_length[IKL_MAX_LINKS];
+  float static_obstacles[IKL_MAX_OBSTACLES][3];   /* (x, y, radius) rows, float32 of the JSON values */
+} IklSpec;
+
+/* Number of constraints / multipliers K = 1 + [JL] J + J * num_obstacles (scripts/trainer.py:72-97).
+ * Order: [EE, JL_1..JL_J, (obstacle 0: j=0..J-1), (obstacle 1: ...), ...], where j indexes the FK
+ * tuple, i.e. j = 0 is the END EFFECTOR tip and j = J-1 the first link's tip (trainer.py:231-240). */
+int32_t ikl_num_constraints(const IklSpec* spec);
+
+/* One batch of inputs to the Lagrangian, as strided views.
+ *   theta    (B, J)        network output; element (b, j) at theta[b*theta_sb + j*theta_sj]
+ *   target   (B, >=2)      q_ee_desired; only x (c=0) and y (c=1) are read (trainer.py:192)
+ *   obstacles(B, n_obs, 3+) per-sample circles (x, y, radius) for dynamic configs, else NULL
+ * Native layouts (vectorised, no re-layout pass):
+ *   "rows"   the reference's own tensors: theta (B,J) contiguous, target (B,3) contiguous,
+ *            obstacles (B,4,4) contiguous [x, y, r, pad]   (kinematics/dataset.py:80-85,143-155)
+ *   "planes" structure-of-arrays: every column its own contiguous plane of B floats with B % 4 == 0
+ *            and 16-byte aligned planes (theta_sb == 1, theta_sj == plane pitch, ...).
+ */
+typedef struct IklBatch {
+  int64_t batch;                                   /* B >= 0 */
+  const float* theta;      int64_t theta_sb, theta_sj;
+  const float* target;     int64_t target_sb, target_sc;
+  const float* obstacles;  int64_t obst_sb, obst_so, obst_sc;
+} IklBatch;
+
+/* Per-constraint weights of the Lagrangian.  Exactly one of the two pointers is non-NULL.
+ *   host:   K floats in host memory, captured by value at launch (they ride in the kernel
+ *           parameters / constant bank: cheapest; use when lambda is known on the host, which it is
+ *           for the whole of train_with_relaxation, trainer.py:251-265);
+ *   device: K floats in device memory, read by the kernel (no host sync needed). */
+typedef struct IklWeights {
+  const float* host;
+  const float* device;
+} IklWeights;
+
+/* Bytes of device workspace any launch on a batch of this size may need.  The workspace must be
+ * zero-filled once after allocation; the library leaves it consistent after every call. */
+size_t ikl_workspace_bytes(int64_t batch);
+
+/* Forward only: constraint sums and Lagrangian of one batch.
+ * Replaces the FK/penalty part of IkLagrangeDualTrainer.process_batch (scripts/trainer.py:182-247)
+ * as used under no_grad by update_multipliers (:276-278) and validate (:297-301).
+ *   viol_out   [K] float   outputs["constraint_violations"]  (batch SUMS, trainer.py:195,204,239)
+ *   loss_out   [1] float   outputs["lagrange_loss"] = sum_i w_i * viol_i (trainer.py:247)
+ *   viol_accum [K] double  optional running sum over calls (the T.sum(axis=0) of trainer.py:274-280)
+ *   q_ee_out   (B,3) float optional outputs["q_ee_actual"] = (x, y, phi) of the end effector
+ *   err_sq_out (B,2) float optional outputs["position_err_sq"]  (trainer.py:192)
+ */
+IklStatus ikl_lagrangian_forward(const IklSpec* spec, const IklBatch* in, const IklWeights* w,
+                                 void* workspace, float* viol_out, float* loss_out, double* viol_accum,
+                                 float* q_ee_out, float* err_sq_out, void* stream);
+
+/* One pass that produces the sums AND d(sum_i w_i g_i)/d(theta) analytically (no autograd tape).
+ * Replaces process_batch (trainer.py:182-247) followed by lagrange_loss.backward() down to the
+ * network output (trainer.py:264).  dtheta element (b, j) is written at dtheta[b*dtheta_sb + j*dtheta_sj].
+ * Gradient conventions at the non-smooth points follow torch autograd (max ties split evenly,
+ * sign(0) = 0); at a circle centre (d == 0) the direction term is 0 where torch gives NaN. */
+IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w,
+                                          void* workspace, float* viol_out, float* loss_out, double* viol_accum,
+                                          float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj, void* stream);
+
+/* lambda <- max(0, lambda + multiplier_lr * viol_sum)   (scripts/trainer.py:280-284, update_multipliers).
+ * viol_sum is the double running sum filled through viol_accum (or NULL to use viol_sum_f32).
+ * lam_out may alias lam_in. */
+IklStatus ikl_dual_update(const float* lam_in, const double* viol_sum, const float* viol_sum_f32,
+                          float multiplier_lr, int32_t num_constraints, float* lam_out, void* stream);
+
+/* ---- function-level drop-ins (let an unchanged scripts/trainer.py reach CUDA op by op) ---------- */
+
+/* kinematics/forward_kinematics.py:47-83 ForwardKinematicsThreeLinkTorch (and the 2-link maths of :7-22).
+ * tips_out: J contiguous (B,3) blocks, END EFFECTOR FIRST: block k holds tip J-k as (x, y, cumulative angle). */
+IklStatus ikl_fk_forward(const float* theta, int64_t theta_sb, int64_t theta_sj, int64_t batch,
+                         int32_t num_links, const float* link_length_host, float* tips_out, void* stream);
+
+/* Backward of the above: grad_tips has the layout of tips_out (NULL blocks are not supported; pass zeros);
+ * writes dtheta (B,J) contiguous. */
+IklStatus ikl_fk_backward(const float* theta, int64_t theta_sb, int64_t theta_sj, int64_t batch,
+                          int32_t num_links, const float* link_length_host, const float* grad_tips,
+                          float* dtheta, void* stream);
+
+/* kinematics/penalties.py:5-17 piecewise_circle_penalty, elementwise over n broadcast elements.
+ * Each operand is a 1-D strided view (stride 0 = broadcast).  Bit-exact with the reference's fp32
+ * arithmetic (same roundings: no FMA contraction, IEEE sqrt). */
+IklStatus ikl_circle_penalty_forward(const float* jx, int64_t s_jx, const float* jy, int64_t s_jy,
+                                     const float* ox, int64_t s_ox, const float* oy, int64_t s_oy,
+                                     const float* radius, int64_t s_r, int64_t n,
+                                     float inside_slope, float outside_slope, float* out, void* stream);
+
+/* Backward: grad_out (n, contiguous) -> d/djx, d/djy (n, contiguous; either may be NULL), and optionally
+ * d/dox, d/doy, d/dradius per element (caller reduces over broadcast dims). */
+IklStatus ikl_circle_penalty_backward(const float* jx, int64_t s_jx, const float* jy, int64_t s_jy,
+                                      const float* ox, int64_t s_ox, const float* oy, int64_t s_oy,
+                                      const float* radius, int64_t s_r, int64_t n,
+                                      float inside_slope, float outside_slope, const float* grad_out,
+                                      float* d_jx, float* d_jy, float* d_ox, float* d_oy, float* d_radius,
+                                      void* stream);
+
+/* kinematics/penalties.py:44-56 piecewise_joint_limit_penalty, elementwise, same conventions. */
+IklStatus ikl_joint_limit_penalty_forward(const float* theta, int64_t s_t, const float* lo, int64_t s_lo,
+                                          const float* hi, int64_t s_hi, int64_t n,
+                                          float inside_slope, float outside_slope, float* out, void* stream);
+
+IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, const float* lo, int64_t s_lo,
+                                           const float* hi, int64_t s_hi, int64_t n,
+                                           float inside_slope, float outside_slope, const float* grad_out,
+                                           float* d_theta, float* d_lo, float* d_hi, void* stream);
+
+/* ---- housekeeping ------------------------------------------------------------------------------ */
+int32_t ikl_abi_version(void);
+const char* ikl_strerror(IklStatus status);
+int32_t ikl_last_cuda_error(void);
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+int64_t ikl_launch_count(void);
+/* Name of the kernel variant the last ikl_lagrangian_* call on this thread dispatched to. */
+const char* ikl_last_kernel_name(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* IKL_H_ */

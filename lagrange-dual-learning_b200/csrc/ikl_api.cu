@@ -1,0 +1,219 @@
+// ikl_api.cu -- C ABI of the fused Lagrangian path (include/ikl.h): argument validation, layout
+// detection, constant preparation and dispatch to the kernel families.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "ikl_lagrangian.cuh"
+
+namespace ikl {
+
+namespace {
+thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+thread_local const char* g_last_kernel = "";
+std::atomic<long long> g_launches{0};
+
+constexpr int kMaxGrid = 2048;                                       // upper bound on persistent grid size
+constexpr size_t kPartialsBytes = (size_t)kMaxGrid * kMaxK * sizeof(double);
+constexpr size_t kWorkspaceBytes = kPartialsBytes + 256;             // + the completion counter
+}  // namespace
+
+void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+void set_last_kernel_name(const char* name) { g_last_kernel = name; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int forced_layout() {
+  const char* e = getenv("IKL_FORCE_LAYOUT");
+  if (!e || !*e) return -1;
+  if (!strcmp(e, "strided")) return kStrided;
+  if (!strcmp(e, "rows")) return kRows;
+  if (!strcmp(e, "planes")) return kPlanes;
+  return -1;
+}
+
+IklStatus validate(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, const float* viol_out,
+                   const float* loss_out) {
+  if (!spec || !in || !w || !workspace || !viol_out || !loss_out) return IKL_ERR_INVALID_ARGUMENT;
+  if (spec->num_links < 1 || spec->num_obstacles < 0 || in->batch < 0) return IKL_ERR_INVALID_ARGUMENT;
+  if (spec->num_links != 2 && spec->num_links != 3) return IKL_ERR_UNSUPPORTED;
+  if (spec->num_obstacles > IKL_MAX_OBSTACLES) return IKL_ERR_UNSUPPORTED;
+  if (!(spec->good_slope >= 0.f) || !(spec->bad_slope >= 0.f)) return IKL_ERR_INVALID_ARGUMENT;   // penalties.py:10,49
+  if ((w->host == nullptr) == (w->device == nullptr)) return IKL_ERR_INVALID_ARGUMENT;
+  if (in->batch > 0) {
+    if (!in->theta || !in->target) return IKL_ERR_INVALID_ARGUMENT;
+    if (spec->num_obstacles > 0 && spec->dynamic_obstacles && !in->obstacles) return IKL_ERR_INVALID_ARGUMENT;
+  }
+  return IKL_OK;
+}
+
+void fill_uniforms(const IklSpec* spec, const float* w_host, Uniforms& u) {
+  memset(&u, 0, sizeof(u));
+  const int J = spec->num_links;
+  for (int m = 0; m < kMaxLinks; ++m) u.link[m] = m < J ? spec->link_length[m] : 1.0f;
+  const float lo = spec->limit_lo, hi = spec->limit_hi;
+  // penalties.py:51-52 in fp32, the way torch evaluates them on float32 tensors
+  u.jl_mid = (lo + hi) / 2.0f;
+  const float rng = fabsf(hi - lo);
+  u.jl_in = spec->good_slope;          // trainer.py:203-204: inside = good, outside = bad
+  u.jl_out = spec->bad_slope;
+  u.jl_cin = (u.jl_in * 0.5f) * rng;   // penalties.py:53: inside_slope*0.5 is folded first, then * limit_range
+  u.jl_cout = (u.jl_out * 0.5f) * rng;
+  u.ob_hi = fmaxf(spec->good_slope, spec->bad_slope);
+  u.ob_lo = fminf(spec->good_slope, spec->bad_slope);
+  for (int o = 0; o < kMaxObst; ++o)
+    for (int c = 0; c < 3; ++c) u.stat_ob[o][c] = spec->static_obstacles[o][c];
+  if (w_host) {
+    const int K = ikl_num_constraints(spec);
+    for (int i = 0; i < K; ++i) u.w[i] = w_host[i];
+    int idx = 1;
+    if (spec->enforce_joint_limits) {
+      for (int j = 0; j < J; ++j, ++idx) {
+        u.w_jl_in[j] = u.w[idx] * u.jl_in;
+        u.w_jl_out[j] = u.w[idx] * u.jl_out;
+        u.w_jl_tie[j] = u.w[idx] * (0.5f * (u.jl_in + u.jl_out));
+      }
+    }
+    for (int q = 0; q < J * spec->num_obstacles; ++q, ++idx) {
+      u.w_ob_hi[q] = -u.w[idx] * u.ob_hi;
+      u.w_ob_lo[q] = -u.w[idx] * u.ob_lo;
+      u.w_ob_tie[q] = -u.w[idx] * (0.5f * (u.ob_hi + u.ob_lo));
+    }
+  }
+}
+
+bool unit_links(const IklSpec* spec) {
+  for (int m = 0; m < spec->num_links; ++m)
+    if (spec->link_length[m] != 1.0f) return false;
+  return true;
+}
+
+// Which vectorised layout (if any) the strides describe.  batch == 1 always takes the strided kernel.
+int detect_layout(const IklSpec* spec, const IklBatch* in, bool grad, const float* dtheta, int64_t dt_sb, int64_t dt_sj) {
+  const int J = spec->num_links;
+  const bool dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles;
+  if (J != 3 || !unit_links(spec) || in->batch < 2) return kStrided;
+  const bool rows = in->theta_sj == 1 && in->theta_sb == J && in->target_sc == 1 && in->target_sb >= 2 &&
+                    (!dyn || (in->obst_sc == 1 && in->obst_so == 4 && in->obst_sb == 4 * kMaxObst && aligned16(in->obstacles))) &&
+                    (!grad || (dt_sj == 1 && dt_sb == J));
+  if (rows) return kRows;
+  constexpr int V = IKL_PLANES_VEC;
+  const bool planes = in->theta_sb == 1 && in->target_sb == 1 && in->batch % V == 0 && aligned16(in->theta) && in->theta_sj % 4 == 0 &&
+                      aligned16(in->target) && in->target_sc % 4 == 0 &&
+                      (!dyn || (in->obst_sb == 1 && aligned16(in->obstacles) && in->obst_so % 4 == 0 && in->obst_sc % 4 == 0)) &&
+                      (!grad || (dt_sb == 1 && dt_sj % 4 == 0 && aligned16(dtheta)));
+  if (planes) return kPlanes;
+  return kStrided;
+}
+
+IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
+              double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
+              void* stream) {
+  IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
+  if (st != IKL_OK) return st;
+  if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
+
+  LagrangianParams p;
+  memset(&p, 0, sizeof(p));
+  fill_uniforms(spec, w->host, p.u);
+  p.batch = in->batch;
+  p.theta = in->theta;    p.th_sb = in->theta_sb;  p.th_sj = in->theta_sj;
+  p.target = in->target;  p.tg_sb = in->target_sb; p.tg_sc = in->target_sc;
+  p.obst = in->obstacles; p.ob_sb = in->obst_sb;   p.ob_so = in->obst_so;  p.ob_sc = in->obst_sc;
+  p.dtheta = dtheta;      p.dt_sb = dt_sb;         p.dt_sj = dt_sj;
+  p.q_ee = q_ee_out;
+  p.err_sq = err_sq_out;
+  p.w_dev = w->device;
+  p.partials = reinterpret_cast<double*>(workspace);
+  p.counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + kPartialsBytes);
+  p.viol_out = viol_out;
+  p.loss_out = loss_out;
+  p.viol_accum = viol_accum;
+
+  Variant v;
+  v.nobs = spec->num_obstacles;
+  v.dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles != 0;
+  v.jl = spec->enforce_joint_limits != 0;
+  v.mode = !grad ? kFwd : (w->host ? kGradHostW : kGradDevW);
+
+  int layout = detect_layout(spec, in, grad, dtheta, dt_sb, dt_sj);
+  const int forced = forced_layout();
+  if (forced == kStrided) layout = kStrided;                 // the generic kernel accepts anything
+  else if (forced >= 0 && forced != layout) return IKL_ERR_INVALID_ARGUMENT;   // tests: demand a fast layout or fail loudly
+
+  cudaStream_t cs = (cudaStream_t)stream;
+  bool found = false;
+  cudaError_t e = cudaSuccess;
+  if (layout == kRows) e = launch_family<kRows, 3, true>(v, p, cs, kMaxGrid, &found);
+  else if (layout == kPlanes) e = launch_family<kPlanes, 3, true>(v, p, cs, kMaxGrid, &found);
+  if (!found) {
+    if (forced == kRows || forced == kPlanes) return IKL_ERR_UNSUPPORTED;
+    if (spec->num_links == 3) e = launch_family<kStrided, 3, false>(v, p, cs, kMaxGrid, &found);
+    else e = launch_family<kStrided, 2, false>(v, p, cs, kMaxGrid, &found);
+    if (!found) return IKL_ERR_UNSUPPORTED;
+  }
+  return cuda_status(e);
+}
+
+}  // namespace
+}  // namespace ikl
+
+using namespace ikl;
+
+extern "C" {
+
+int32_t ikl_num_constraints(const IklSpec* spec) {
+  if (!spec) return -1;
+  return 1 + (spec->enforce_joint_limits ? spec->num_links : 0) + spec->num_links * spec->num_obstacles;
+}
+
+size_t ikl_workspace_bytes(int64_t batch) {
+  (void)batch;          // the persistent grid is bounded, so the workspace does not grow with the batch
+  return kWorkspaceBytes;
+}
+
+IklStatus ikl_lagrangian_forward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out,
+                                 float* loss_out, double* viol_accum, float* q_ee_out, float* err_sq_out, void* stream) {
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, q_ee_out, err_sq_out, nullptr, 0, 0, false, stream);
+}
+
+IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out,
+                                          float* loss_out, double* viol_accum, float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
+                                          void* stream) {
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream);
+}
+
+int32_t ikl_abi_version(void) { return IKL_ABI_VERSION; }
+
+const char* ikl_strerror(IklStatus status) {
+  switch (status) {
+    case IKL_OK: return "ok";
+    case IKL_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case IKL_ERR_UNSUPPORTED: return "unsupported configuration";
+    case IKL_ERR_CUDA: return "CUDA error";
+  }
+  return "unknown status";
+}
+
+int32_t ikl_last_cuda_error(void) { return (int32_t)g_last_cuda_error; }
+int64_t ikl_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+const char* ikl_last_kernel_name(void) { return g_last_kernel; }
+
+}  // extern "C"

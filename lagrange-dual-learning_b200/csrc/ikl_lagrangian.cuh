@@ -1,0 +1,388 @@
+// ikl_lagrangian.cuh -- the fused FK + penalty + Lagrangian (+ analytic gradient) kernels.
+//
+// One persistent grid streams the batch once: per sample it reads theta, the target and the obstacle
+// rows, evaluates every constraint term (ikl_device.cuh), optionally writes d(sum_i w_i g_i)/d(theta),
+// and keeps K running sums per thread.  Sums go thread(fp32, short runs) -> thread(fp64) -> warp
+// shuffle -> block -> one fp64 partial per block per constraint -> the last block to finish adds the
+// partials in a fixed order, so results are bit-reproducible for a given launch geometry and no float
+// atomics are used.  (Reference: scripts/trainer.py:182-247 + :264 of miloknowles/lagrange-dual-learning.)
+//
+// Memory layouts (see IklBatch in include/ikl.h):
+//   kStrided  any element strides, scalar loads, runtime link lengths        -- always-correct fallback
+//   kRows     the reference's own row-major tensors: theta (B,J), target (B,>=2), obstacles (B,4,4)
+//             read as one float4 per obstacle row; one sample per thread, U samples in flight
+//   kPlanes   structure-of-arrays planes: kVec consecutive samples per thread, 16-byte loads/stores
+#pragma once
+
+#include "ikl_common.h"
+#include "ikl_device.cuh"
+
+namespace ikl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kFlushEvery = 8;      // outer iterations between fp32 -> fp64 accumulator flushes
+constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce
+
+#ifndef IKL_PLANES_VEC
+#define IKL_PLANES_VEC 4
+#endif
+#ifndef IKL_ROWS_UNROLL
+#define IKL_ROWS_UNROLL 2
+#endif
+#ifndef IKL_MIN_BLOCKS
+#define IKL_MIN_BLOCKS 2
+#endif
+
+enum Layout : int { kStrided = 0, kRows = 1, kPlanes = 2 };
+enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
+
+struct LagrangianParams {
+  Uniforms u;
+  long long batch;
+  const float* theta;   long long th_sb, th_sj;
+  const float* target;  long long tg_sb, tg_sc;
+  const float* obst;    long long ob_sb, ob_so, ob_sc;
+  float* dtheta;        long long dt_sb, dt_sj;
+  float* q_ee;          // (B,3) or null
+  float* err_sq;        // (B,2) or null
+  const float* w_dev;   // K weights in device memory (kGradDevW, or the loss of a kFwd launch) or null
+  double* partials;     // [gridDim.x][kMaxK]
+  unsigned int* counter;
+  float* viol_out;
+  float* loss_out;
+  double* viol_accum;   // or null
+};
+
+template <int LAYOUT_, int J_, int NOBS_, bool DYN_, bool JL_, int MODE_, bool UNIT_>
+struct Cfg {
+  static constexpr int LAYOUT = LAYOUT_, J = J_, NOBS = NOBS_, MODE = MODE_;
+  static constexpr bool DYN = DYN_, JL = JL_, UNIT = UNIT_, GRAD = MODE_ != kFwd;
+  static constexpr int K = num_constraints(J_, NOBS_, JL_);
+  static constexpr int NOB = NOBS_ > 0 ? NOBS_ : 1;
+};
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// ---- reduction tail ----------------------------------------------------------------------------------
+template <int K, bool WDEV>
+__device__ __forceinline__ void finalize_sums(const LagrangianParams& p, double (&dacc)[K]) {
+  __shared__ double s_red[kWarps][kMaxK];
+  __shared__ double s_fin[kFinalParts][kMaxK];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double v = dacc[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < K) {
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < kWarps; ++wq) v += s_red[wq][tid];
+    p.partials[(size_t)blockIdx.x * kMaxK + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int i = tid % kMaxK, part = tid / kMaxK;
+    double v = 0.0;
+    if (i < K)
+      for (unsigned blk = part; blk < gridDim.x; blk += kFinalParts) v += __ldcg(p.partials + (size_t)blk * kMaxK + i);
+    s_fin[part][i] = v;
+  }
+  __syncthreads();
+  if (tid < K) {
+    double tot = 0.0;
+#pragma unroll
+    for (int part = 0; part < kFinalParts; ++part) tot += s_fin[part][tid];
+    p.viol_out[tid] = (float)tot;
+    if (p.viol_accum) p.viol_accum[tid] += tot;
+    const float wi = (p.w_dev != nullptr) ? p.w_dev[tid] : p.u.w[tid];
+    s_fin[0][tid] = tot * (double)wi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double loss = 0.0;
+    for (int i = 0; i < K; ++i) loss += s_fin[0][i];
+    *p.loss_out = (float)loss;
+    *p.counter = 0u;            // leave the workspace ready for the next launch
+  }
+}
+
+// ---- per-sample IO for the one-sample-per-thread layouts ----------------------------------------------------
+template <class C>
+__device__ __forceinline__ void load_sample(const LagrangianParams& p, long long b, float (&th)[C::J], float& tx, float& ty,
+                                            float (&ob)[C::NOB][3]) {
+  if (C::LAYOUT == kRows) {
+    const float* t = p.theta + b * C::J;
+#pragma unroll
+    for (int j = 0; j < C::J; ++j) th[j] = ldg_stream1(t + j);
+    const float* g = p.target + b * p.tg_sb;
+    tx = ldg_stream1(g);
+    ty = ldg_stream1(g + 1);
+    if (C::DYN) {
+      const float* o = p.obst + b * (4 * kMaxObst);
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+        const float4 v = ldg_stream4(o + 4 * k);
+        ob[k][0] = v.x; ob[k][1] = v.y; ob[k][2] = v.z;
+      }
+    }
+  } else {
+    const float* t = p.theta + b * p.th_sb;
+#pragma unroll
+    for (int j = 0; j < C::J; ++j) th[j] = __ldg(t + j * p.th_sj);
+    const float* g = p.target + b * p.tg_sb;
+    tx = __ldg(g);
+    ty = __ldg(g + p.tg_sc);
+    if (C::DYN) {
+      const float* o = p.obst + b * p.ob_sb;
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ob[k][c] = __ldg(o + k * p.ob_so + c * p.ob_sc);
+      }
+    }
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void static_obstacles(const LagrangianParams& p, float (&ob)[C::NOB][3]) {
+#pragma unroll
+  for (int k = 0; k < C::NOB; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ob[k][c] = p.u.stat_ob[k][c];
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void store_sample(const LagrangianParams& p, long long b, const float (&dth)[C::J], const float (&ee)[3],
+                                             float tx, float ty) {
+  if (C::GRAD) {
+    if (C::LAYOUT == kRows) {
+      float* d = p.dtheta + b * C::J;
+#pragma unroll
+      for (int j = 0; j < C::J; ++j) d[j] = dth[j];
+    } else {
+      float* d = p.dtheta + b * p.dt_sb;
+#pragma unroll
+      for (int j = 0; j < C::J; ++j) d[j * p.dt_sj] = dth[j];
+    }
+  } else {
+    if (p.q_ee) {
+      float* q = p.q_ee + b * 3;
+      q[0] = ee[0]; q[1] = ee[1]; q[2] = ee[2];
+    }
+    if (p.err_sq) {
+      const float ex = tx - ee[0], ey = ty - ee[1];
+      p.err_sq[b * 2] = 0.5f * (ex * ex);
+      p.err_sq[b * 2 + 1] = 0.5f * (ey * ey);
+    }
+  }
+}
+
+template <class C, class W>
+__device__ __forceinline__ void run_scalar_layout(const LagrangianParams& p, const W& w, double (&dacc)[C::K]) {
+  constexpr int U = IKL_ROWS_UNROLL;
+  const long long B = p.batch;
+  const long long step = (long long)gridDim.x * (kThreads * U);
+  float acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
+  int since_flush = 0;
+  for (long long base = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; base < B; base += step) {
+    float th[U][C::J], tx[U], ty[U], ob[U][C::NOB][3];
+#pragma unroll
+    for (int uu = 0; uu < U; ++uu) {
+      const long long b = base + uu * kThreads;
+      if (!C::DYN) static_obstacles<C>(p, ob[uu]);
+      if (b < B) load_sample<C>(p, b, th[uu], tx[uu], ty[uu], ob[uu]);
+    }
+#pragma unroll
+    for (int uu = 0; uu < U; ++uu) {
+      const long long b = base + uu * kThreads;
+      if (b < B) {
+        float dth[C::J], ee[3];
+        eval_sample<C::J, C::NOBS, C::JL, C::GRAD, C::UNIT>(p.u, w, th[uu], tx[uu], ty[uu], ob[uu], acc, dth, ee);
+        store_sample<C>(p, b, dth, ee, tx[uu], ty[uu]);
+      }
+    }
+    if (++since_flush == kFlushEvery) {
+      since_flush = 0;
+#pragma unroll
+      for (int i = 0; i < C::K; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) dacc[i] += (double)acc[i];
+}
+
+// ---- planes layout: kVec consecutive samples per thread, 16-byte (or 8-byte) accesses ------------------------
+template <int V> struct VecIO;
+template <> struct VecIO<4> {
+  using T = float4;
+  static __device__ __forceinline__ T load(const float* p) { return ldg_stream4(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  }
+  static __device__ __forceinline__ float get(const T& t, int i) { return i == 0 ? t.x : i == 1 ? t.y : i == 2 ? t.z : t.w; }
+};
+template <> struct VecIO<2> {
+  using T = float2;
+  static __device__ __forceinline__ T load(const float* p) { return ldg_stream2(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+  }
+  static __device__ __forceinline__ float get(const T& t, int i) { return i == 0 ? t.x : t.y; }
+};
+
+template <class C, class W>
+__device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w, double (&dacc)[C::K]) {
+  constexpr int V = IKL_PLANES_VEC;
+  using IO = VecIO<V>;
+  const long long nvec = p.batch / V;             // the API guarantees batch % V == 0 for this layout
+  const long long step = (long long)gridDim.x * kThreads;
+  float acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
+  int since_flush = 0;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += step) {
+    const long long b = v * V;
+    typename IO::T th4[C::J], tg4[2], ob4[C::NOB][3];
+#pragma unroll
+    for (int j = 0; j < C::J; ++j) th4[j] = IO::load(p.theta + j * p.th_sj + b);
+    tg4[0] = IO::load(p.target + b);
+    tg4[1] = IO::load(p.target + p.tg_sc + b);
+    if (C::DYN) {
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ob4[k][c] = IO::load(p.obst + k * p.ob_so + c * p.ob_sc + b);
+      }
+    }
+    float out[C::J][V], eeo[3][V];
+#pragma unroll
+    for (int sidx = 0; sidx < V; ++sidx) {
+      float th[C::J], ob[C::NOB][3], dth[C::J], ee[3];
+#pragma unroll
+      for (int j = 0; j < C::J; ++j) th[j] = IO::get(th4[j], sidx);
+      if (C::DYN) {
+#pragma unroll
+        for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) ob[k][c] = IO::get(ob4[k][c], sidx);
+        }
+      } else {
+        static_obstacles<C>(p, ob);
+      }
+      const float tx = IO::get(tg4[0], sidx), ty = IO::get(tg4[1], sidx);
+      eval_sample<C::J, C::NOBS, C::JL, C::GRAD, C::UNIT>(p.u, w, th, tx, ty, ob, acc, dth, ee);
+      if (C::GRAD) {
+#pragma unroll
+        for (int j = 0; j < C::J; ++j) out[j][sidx] = dth[j];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) eeo[c][sidx] = ee[c];
+      }
+    }
+    if (C::GRAD) {
+#pragma unroll
+      for (int j = 0; j < C::J; ++j) IO::store(p.dtheta + j * p.dt_sj + b, out[j]);
+    } else {
+      if (p.q_ee) {                               // row-major (B,3) / (B,2) side outputs, rarely requested
+#pragma unroll
+        for (int sidx = 0; sidx < V; ++sidx) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p.q_ee[(b + sidx) * 3 + c] = eeo[c][sidx];
+        }
+      }
+      if (p.err_sq) {
+#pragma unroll
+        for (int sidx = 0; sidx < V; ++sidx) {
+          const float ex = IO::get(tg4[0], sidx) - eeo[0][sidx], ey = IO::get(tg4[1], sidx) - eeo[1][sidx];
+          p.err_sq[(b + sidx) * 2] = 0.5f * (ex * ex);
+          p.err_sq[(b + sidx) * 2 + 1] = 0.5f * (ey * ey);
+        }
+      }
+    }
+    if (++since_flush == kFlushEvery) {
+      since_flush = 0;
+#pragma unroll
+      for (int i = 0; i < C::K; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) dacc[i] += (double)acc[i];
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
+  double dacc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) dacc[i] = 0.0;
+  if (C::MODE == kGradDevW) {
+    const DeviceWeights<C::K> w(p.u, p.w_dev);
+    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, dacc); else run_scalar_layout<C>(p, w, dacc);
+  } else {
+    const HostWeights w(p.u, nullptr);
+    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, dacc); else run_scalar_layout<C>(p, w, dacc);
+  }
+  finalize_sums<C::K, C::MODE == kGradDevW>(p, dacc);
+}
+
+// ---- host-side launch ------------------------------------------------------------------------------------------
+template <class C>
+cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks, const char* name) {
+  static int blocks_per_sm = 0;      // per instantiation; same answer on every device of a homogeneous node
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_kernel<C>, kThreads, 0);
+    if (e != cudaSuccess) return e;
+    blocks_per_sm = n > 0 ? n : 1;
+  }
+  const long long per_block = (long long)kThreads * (C::LAYOUT == kPlanes ? IKL_PLANES_VEC : IKL_ROWS_UNROLL);
+  long long tiles = (p.batch + per_block - 1) / per_block;
+  if (tiles < 1) tiles = 1;
+  long long grid = (long long)sm_count() * blocks_per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid > max_blocks) grid = max_blocks;
+  set_last_kernel_name(name);
+  count_launch();
+  lagrangian_kernel<C><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Key of a specialisation inside one (LAYOUT, J, UNIT) family.
+struct Variant {
+  int nobs;
+  bool dyn, jl;
+  int mode;
+};
+
+// Instantiated once per family in ikl_lagrangian_<family>.cu.
+template <int LAYOUT, int J, bool UNIT>
+cudaError_t launch_family(const Variant& v, const LagrangianParams& p, cudaStream_t stream, int max_blocks, bool* found);
+
+}  // namespace ikl

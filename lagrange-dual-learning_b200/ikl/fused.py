@@ -1,0 +1,228 @@
+"""PyTorch-facing side of the fused IK Lagrangian (level (ii) of the drop-in boundary).
+
+  lagrangian_forward            constraint sums + Lagrangian of a batch          (trainer.py:182-247 under no_grad)
+  lagrangian_forward_backward   the same plus d(loss)/d(theta) in the same pass  (trainer.py:182-247 + :264)
+  FusedIkLagrangian             torch.autograd.Function wrapping the two
+  dual_update                   lambda <- max(0, lambda + lr * sum)              (trainer.py:280-284)
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libikl.so (sm_100a CUDA),
+reached through the C ABI in include/ikl.h.  There is no CPU fallback: CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from .spec import ConstraintSpec
+
+_workspaces = {}
+
+
+def _require_cuda_f32(t, name):
+  if not isinstance(t, torch.Tensor):
+    raise TypeError("%s must be a torch.Tensor" % name)
+  if not t.is_cuda:
+    raise RuntimeError("%s is on %s: the fused IK Lagrangian runs on CUDA only (no CPU fallback)" % (name, t.device))
+  if t.dtype != torch.float32:
+    raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+  return t
+
+
+def _stream_ptr(device):
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(device):
+  """One zero-initialised workspace per (device, stream): launches on a stream are ordered, so it is reused."""
+  key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+  ws = _workspaces.get(key)
+  if ws is None:
+    ws = torch.zeros(int(_cabi.load().ikl_workspace_bytes(0)), dtype=torch.uint8, device=device)
+    _workspaces[key] = ws
+  return ws
+
+
+class _Weights(object):
+  """IklWeights from a tensor/sequence: CUDA tensor -> read on device; anything on the host -> by value."""
+
+  def __init__(self, lam, K, device):
+    self.c = _cabi.IklWeights()
+    self.keep = None
+    if isinstance(lam, torch.Tensor) and lam.is_cuda:
+      lam = _require_cuda_f32(lam, "lam")
+      if lam.numel() != K:
+        raise ValueError("lam has %d entries, the configuration has %d constraints" % (lam.numel(), K))
+      self.keep = lam.contiguous()
+      self.c.host = None
+      self.c.device = self.keep.data_ptr()
+    else:
+      vals = [float(v) for v in (lam.tolist() if isinstance(lam, torch.Tensor) else lam)]
+      if len(vals) != K:
+        raise ValueError("lam has %d entries, the configuration has %d constraints" % (len(vals), K))
+      self.keep = (ctypes.c_float * K)(*vals)
+      self.c.host = ctypes.cast(self.keep, ctypes.POINTER(ctypes.c_float))
+      self.c.device = None
+
+
+def _batch_desc(spec, theta, q_ee_desired, obstacles):
+  theta = _require_cuda_f32(theta, "theta")
+  q_ee_desired = _require_cuda_f32(q_ee_desired, "q_ee_desired")
+  if theta.dim() != 2 or theta.shape[1] != spec.num_links:
+    raise ValueError("theta must be (B, %d), got %s" % (spec.num_links, tuple(theta.shape)))
+  B = theta.shape[0]
+  if q_ee_desired.dim() != 2 or q_ee_desired.shape[0] != B or q_ee_desired.shape[1] < 2:
+    raise ValueError("q_ee_desired must be (B, >=2), got %s" % (tuple(q_ee_desired.shape),))
+  if q_ee_desired.device != theta.device:
+    raise ValueError("theta and q_ee_desired live on different devices")
+  d = _cabi.IklBatch()
+  d.batch = B
+  d.theta, d.theta_sb, d.theta_sj = theta.data_ptr(), theta.stride(0), theta.stride(1)
+  d.target, d.target_sb, d.target_sc = q_ee_desired.data_ptr(), q_ee_desired.stride(0), q_ee_desired.stride(1)
+  if spec.dynamic:
+    if obstacles is None:
+      raise ValueError("this configuration has dynamic obstacles: pass the (B, n_obs, >=3) obstacle tensor")  # trainer.py:211
+    obstacles = _require_cuda_f32(obstacles, "obstacles")
+    if obstacles.dim() != 3 or obstacles.shape[0] != B or obstacles.shape[1] < spec.num_obstacles or obstacles.shape[2] < 3:
+      raise ValueError("obstacles must be (B, >=%d, >=3), got %s" % (spec.num_obstacles, tuple(obstacles.shape)))
+    d.obstacles = obstacles.data_ptr()
+    d.obst_sb, d.obst_so, d.obst_sc = obstacles.stride()
+  else:
+    d.obstacles, d.obst_sb, d.obst_so, d.obst_sc = None, 0, 0, 0
+  return d, (theta, q_ee_desired, obstacles)
+
+
+def _check_accum(viol_accum, K, device):
+  if viol_accum is None:
+    return None
+  if not (viol_accum.is_cuda and viol_accum.dtype == torch.float64 and viol_accum.is_contiguous() and viol_accum.numel() >= K):
+    raise ValueError("viol_accum must be a contiguous CUDA float64 tensor with >= K entries")
+  return ctypes.c_void_p(viol_accum.data_ptr())
+
+
+def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, want_q_ee=False,
+                       want_err_sq=False):
+  """Constraint sums and Lagrangian of one batch, forward only.
+
+  Returns a dict with the reference's output keys: constraint_violations (K,), lagrange_loss (),
+  and optionally q_ee_actual (B,3), position_err_sq (B,2)   (scripts/trainer.py:184,193,244,247).
+  ``viol_accum`` (K float64 on device) is incremented by the sums: the running total update_multipliers needs.
+  """
+  lib = _cabi.load()
+  K = spec.num_constraints
+  desc, keep = _batch_desc(spec, theta, q_ee_desired, obstacles)
+  dev = theta.device
+  w = _Weights(lam if lam is not None else [0.0] * K, K, dev)
+  with torch.cuda.device(dev):
+    out = torch.empty(K + 1, dtype=torch.float32, device=dev)
+    B = theta.shape[0]
+    q_ee = torch.empty(B, 3, dtype=torch.float32, device=dev) if want_q_ee else None
+    err = torch.empty(B, 2, dtype=torch.float32, device=dev) if want_err_sq else None
+    st = lib.ikl_lagrangian_forward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                    ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                    ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+                                    ctypes.c_void_p(q_ee.data_ptr()) if want_q_ee else None,
+                                    ctypes.c_void_p(err.data_ptr()) if want_err_sq else None, _stream_ptr(dev))
+  _cabi.check(st, "ikl_lagrangian_forward")
+  res = {"constraint_violations": out[:K], "lagrange_loss": out[K]}
+  if want_q_ee:
+    res["q_ee_actual"] = q_ee
+  if want_err_sq:
+    res["position_err_sq"] = err
+  return res
+
+
+def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, dtheta=None):
+  """One pass: (constraint_violations (K,), lagrange_loss (), dtheta (B,J)) with dtheta = d(sum_i lam_i g_i)/d(theta)."""
+  lib = _cabi.load()
+  K = spec.num_constraints
+  if lam is None:
+    raise ValueError("lam (the K multipliers / weights) is required for the gradient")
+  desc, keep = _batch_desc(spec, theta, q_ee_desired, obstacles)
+  dev = theta.device
+  w = _Weights(lam, K, dev)
+  with torch.cuda.device(dev):
+    out = torch.empty(K + 1, dtype=torch.float32, device=dev)
+    if dtheta is None:
+      # same memory layout as theta when it is dense (rows or planes); otherwise row-major
+      dense = theta.is_contiguous() or theta.t().is_contiguous()
+      dtheta = torch.empty_strided(theta.shape, theta.stride(), dtype=torch.float32, device=dev) if dense else \
+          torch.empty(theta.shape, dtype=torch.float32, device=dev)
+    else:
+      _require_cuda_f32(dtheta, "dtheta")
+      if dtheta.shape != theta.shape:
+        raise ValueError("dtheta must have theta's shape")
+    st = lib.ikl_lagrangian_forward_backward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                             ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                             ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+                                             ctypes.c_void_p(dtheta.data_ptr()), dtheta.stride(0), dtheta.stride(1),
+                                             _stream_ptr(dev))
+  _cabi.check(st, "ikl_lagrangian_forward_backward")
+  return out[:K], out[K], dtheta
+
+
+def dual_update(lam, viol_sum, multiplier_lr, out=None):
+  """lambda <- clamp(lambda + multiplier_lr * viol_sum, min=0)   (scripts/trainer.py:280-284).
+
+  viol_sum: (K,) float64 running sum (from ``viol_accum``) or float32 sum over the validation batches.
+  Returns a NEW tensor unless ``out`` is given (the reference rebinds self.lambda_multipliers, trainer.py:333).
+  """
+  lib = _cabi.load()
+  lam = _require_cuda_f32(lam, "lam").contiguous()
+  K = lam.numel()
+  if not viol_sum.is_cuda or viol_sum.numel() < K or not viol_sum.is_contiguous():
+    raise ValueError("viol_sum must be a contiguous CUDA tensor with K entries")
+  if viol_sum.dtype == torch.float64:
+    v64, v32 = ctypes.c_void_p(viol_sum.data_ptr()), None
+  elif viol_sum.dtype == torch.float32:
+    v64, v32 = None, ctypes.c_void_p(viol_sum.data_ptr())
+  else:
+    raise TypeError("viol_sum must be float64 or float32")
+  if out is None:
+    out = torch.empty_like(lam)
+  with torch.cuda.device(lam.device):
+    st = lib.ikl_dual_update(ctypes.c_void_p(lam.data_ptr()), v64, v32, float(multiplier_lr), K,
+                             ctypes.c_void_p(out.data_ptr()), _stream_ptr(lam.device))
+  _cabi.check(st, "ikl_dual_update")
+  return out
+
+
+class FusedIkLagrangian(torch.autograd.Function):
+  """(constraint_violations[K], lagrange_loss[]) = f(theta, q_ee_desired, obstacles, lam).
+
+  Differentiable w.r.t. theta only (targets, obstacles, limits and lam carry no gradient in the reference).
+  When theta needs a gradient the forward launch already produces d(sum_i lam_i g_i)/d(theta); backward
+  scales it by the incoming gradient of lagrange_loss.  A non-trivial gradient flowing into
+  constraint_violations re-runs the kernel with weights grad_loss*lam + grad_viol.
+  """
+
+  @staticmethod
+  def forward(ctx, theta, q_ee_desired, obstacles, lam, spec, lam_host=None):
+    ctx.set_materialize_grads(False)
+    ctx.spec = spec
+    weights = lam_host if lam_host is not None else lam
+    if ctx.needs_input_grad[0]:
+      viol, loss, dtheta = lagrangian_forward_backward(spec, theta.detach(), q_ee_desired, obstacles, weights)
+      ctx.save_for_backward(theta, q_ee_desired, obstacles if spec.dynamic else None, lam, dtheta)
+    else:
+      out = lagrangian_forward(spec, theta.detach(), q_ee_desired, obstacles, weights)
+      viol, loss = out["constraint_violations"], out["lagrange_loss"]
+    return viol, loss
+
+  @staticmethod
+  def backward(ctx, grad_viol, grad_loss):
+    theta, q_ee_desired, obstacles, lam, dtheta = ctx.saved_tensors
+    if grad_viol is None:
+      if grad_loss is None:
+        return None, None, None, None, None, None
+      return dtheta * grad_loss, None, None, None, None, None
+    lam_dev = lam if (isinstance(lam, torch.Tensor) and lam.is_cuda) else torch.as_tensor(lam, dtype=torch.float32, device=theta.device)
+    w = grad_viol if grad_loss is None else grad_viol + grad_loss * lam_dev
+    _, _, g = lagrangian_forward_backward(ctx.spec, theta.detach(), q_ee_desired, obstacles, w.contiguous())
+    return g, None, None, None, None, None
+
+
+def ik_lagrangian(theta, q_ee_desired, obstacles, lam, spec, lam_host=None):
+  """Functional form of FusedIkLagrangian: returns (constraint_violations, lagrange_loss)."""
+  if not isinstance(lam, torch.Tensor):
+    lam = torch.as_tensor(lam, dtype=torch.float32)
+  return FusedIkLagrangian.apply(theta, q_ee_desired, obstacles, lam, spec, lam_host)

@@ -1,0 +1,457 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors that
+were produced by running the unmodified reference.  Run on the B200 box:  pytest tests -m gpu
+
+TOLERANCE (BASELINE.json north_star: <= 1e-5 relative, fp32):
+  * per-sample quantities (positions, penalties, d/dtheta):  |got - ref| <= 1e-5 * max(|ref|, S) with S the
+    natural scale of the tensor (max |ref| over the batch) -- a pure ratio is meaningless where ref crosses 0;
+  * batch sums g_i: |got - ref| <= 1e-5 * sum_b |term_b,i|  (relative to the sum of magnitudes);
+  * d/dtheta is compared away from the kinks of the piecewise-linear penalties (|t| or ||u|-h| below 1e-6 in
+    the fp64 oracle), where a 1-ulp difference legitimately flips the subgradient; the masked fraction must stay
+    below 1e-3 and the tie conventions themselves are tested on exact hand-made cases.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CONFIG_NAMES, GOLDEN, config_json, golden_npz
+from oracle import ik_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(got, ref, scale=None, rtol=RTOL):
+  got = np.asarray(got, dtype=np.float64)
+  ref = np.asarray(ref, dtype=np.float64)
+  s = float(np.max(np.abs(ref))) if scale is None else float(scale)
+  np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * max(s, 1e-30))
+
+
+def specs_for(name, good=0.005, bad=1.0):
+  from ikl import ConstraintSpec
+  cfg = config_json(name)
+  return ConstraintSpec.from_config(cfg, 3, good, bad), O.spec_from_json(cfg, 3, good, bad)
+
+
+def oracle_truth(ospec, theta, q_des, obst, lam):
+  """fp64 oracle: sums, per-sample terms, closed-form gradient and the near-kink mask."""
+  th, qd, ob = theta.double(), q_des.double(), obst.double()
+  out = O.lagrangian(th, qd, torch.as_tensor(lam).double(), ospec, ob if ospec.dynamic else None, per_sample=True)
+  terms = out["per_sample_terms"].numpy()
+  _, dth = O.lagrangian_grad_closed_form(th.numpy(), qd.numpy(), np.asarray(lam, dtype=np.float64), ospec,
+                                         ob.numpy() if ospec.dynamic else None)
+  kink = (np.abs(terms[:, 1:]) < 1e-6).any(axis=1) if terms.shape[1] > 1 else np.zeros(len(terms), bool)
+  return out["constraint_violations"].numpy(), np.abs(terms).sum(axis=0), dth, kink, out
+
+
+LAYOUTS = ("rows", "planes", "strided")
+
+
+def run_layout(layout, spec, theta, q_des, obst, lam, grad=True, monkeypatch=None):
+  """Run the fused op on CUDA in a given memory layout; returns numpy (viol, loss, dtheta, kernel name)."""
+  from ikl import fused, synthetic, _cabi
+  dev = torch.device("cuda:0")
+  th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+  if layout == "planes":
+    th, qd, ob = synthetic.to_planes(th, qd, ob, max(spec.num_obstacles, 1))
+  if layout == "strided":
+    monkeypatch.setenv("IKL_FORCE_LAYOUT", "strided")
+  else:
+    monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  if grad:
+    viol, loss, dth = fused.lagrangian_forward_backward(spec, th, qd, ob if spec.dynamic else None, lam)
+    dth = dth.cpu().numpy()
+  else:
+    out = fused.lagrangian_forward(spec, th, qd, ob if spec.dynamic else None, lam)
+    viol, loss, dth = out["constraint_violations"], out["lagrange_loss"], None
+  name = _cabi.last_kernel_name()
+  torch.cuda.synchronize()
+  return viol.cpu().numpy(), float(loss.cpu()), dth, name
+
+
+# ------------------------------------------------------------------------------------------------------------
+# level (i): function drop-ins
+# ------------------------------------------------------------------------------------------------------------
+def test_fk_dropin_against_reference_golden(cuda_device):
+  import kinematics.forward_kinematics as fk
+  g = golden_npz("fk.npz")
+  theta = torch.from_numpy(g["theta"]).to(cuda_device)
+  x3, x2, x1 = fk.ForwardKinematicsThreeLinkTorch(theta)
+  small = np.abs(g["theta"]).max(axis=1) < 50          # fp32 range reduction of huge angles is library-specific
+  for got, key in ((x3, "x3"), (x2, "x2"), (x1, "x1")):
+    close(got.cpu().numpy()[small], g[key + "_f64"][small], scale=3.0)
+    close(got.cpu().numpy()[small], g[key][small], scale=3.0)
+    # huge angles: compare with the reference's own fp32 result at fp32 argument accuracy
+    np.testing.assert_allclose(got.cpu().numpy()[~small][:, :2], g[key][~small][:, :2], atol=3e-4)
+  assert x3.shape == (len(g["theta"]), 3) and x3.is_cuda
+
+
+def test_fk_dropin_hand_values_and_cpu_roundtrip(cuda_device):
+  import kinematics.forward_kinematics as fk
+  x3, x2, x1 = fk.ForwardKinematicsThreeLinkTorch(torch.zeros(1, 3))       # CPU in -> CPU out (dataset.py:68)
+  assert not x3.is_cuda
+  assert x1[0].tolist() == [1.0, 0.0, 0.0] and x2[0].tolist() == [2.0, 0.0, 0.0] and x3[0].tolist() == [3.0, 0.0, 0.0]
+  x3, x2, x1 = fk.ForwardKinematicsThreeLinkTorch(torch.tensor([[math.pi / 2, -math.pi / 2, -math.pi / 2]], device=cuda_device))
+  np.testing.assert_allclose(x2[0].cpu().numpy(), [1.0, 1.0, 0.0], atol=1e-6)
+  np.testing.assert_allclose(x3[0].cpu().numpy(), [1.0, 0.0, -math.pi / 2], atol=1e-6)
+  with pytest.raises(AssertionError):
+    fk.ForwardKinematicsThreeLinkTorch(torch.zeros(4, 2, device=cuda_device))
+  with pytest.raises(AssertionError):
+    fk.ForwardKinematicsThreeLinkTorch(torch.zeros(4, device=cuda_device))
+
+
+def test_fk_two_link_against_numpy_reference(cuda_device):
+  import kinematics.forward_kinematics as fk
+  g = golden_npz("fk.npz")
+  th2 = torch.from_numpy(g["theta2"]).float().to(cuda_device)
+  ee, x1 = fk.ForwardKinematicsTwoLinkTorch(th2)
+  close(ee.cpu().numpy(), g["ee2_f64"], scale=2.0)
+  assert np.allclose([float(v) for v in fk.ForwardKinematicsTwoLink(g["theta2"][3])], g["ee2_f64"][3])
+
+
+def test_fk_backward_matches_autograd_of_oracle(cuda_device):
+  import kinematics.forward_kinematics as fk
+  torch.manual_seed(3)
+  theta = (torch.rand(513, 3) * 2 - 1) * 3
+  w = [torch.randn(513, 3) for _ in range(3)]
+  th_ref = theta.double().requires_grad_(True)
+  tips = O.forward_kinematics(th_ref)
+  sum((t * wk.double()).sum() for t, wk in zip(tips, w)).backward()
+  th = theta.to(cuda_device).requires_grad_(True)
+  tips_g = fk.ForwardKinematicsThreeLinkTorch(th)
+  sum((t * wk.to(cuda_device)).sum() for t, wk in zip(tips_g, w)).backward()
+  close(th.grad.cpu().numpy(), th_ref.grad.numpy())
+  # only the end effector used (the trainer's q_ee_actual path): unused outputs get no gradient
+  th2 = theta.to(cuda_device).requires_grad_(True)
+  fk.ForwardKinematicsThreeLinkTorch(th2)[0][:, :2].sum().backward()
+  th_ref2 = theta.double().requires_grad_(True)
+  O.forward_kinematics(th_ref2)[0][:, :2].sum().backward()
+  close(th2.grad.cpu().numpy(), th_ref2.grad.numpy())
+
+
+def test_reference_known_answers_through_dropin(cuda_device):
+  """test/test_training_utils.py:7-41 of the reference, run against the CUDA drop-ins (CPU tensors in, as there)."""
+  import kinematics.penalties as pen
+  jx = torch.Tensor([0.0, 0.5, 0.75, 0.5, -1.0])
+  jy = torch.Tensor([0.0, 0.5, 0.5, 0.75, 0.5])
+  penalty = pen.piecewise_circle_penalty(jx, jy, torch.Tensor([0.5]), torch.Tensor([0.5]), torch.Tensor([0.25]),
+                                         inside_slope=1.0, outside_slope=0.1)
+  torch.testing.assert_close(penalty, torch.Tensor([-0.1 * (math.sqrt(0.5 ** 2 + 0.5 ** 2) - 0.25), 0.25, 0, 0, -0.1 * 1.25]))
+  theta = torch.Tensor([-math.pi, math.pi, 0, 0.1])
+  penalty = pen.piecewise_joint_limit_penalty(theta, torch.Tensor([-2 * math.pi / 3]), torch.Tensor([2 * math.pi / 3]),
+                                              inside_slope=0.1, outside_slope=1.0)
+  torch.testing.assert_close(penalty, torch.Tensor([math.pi / 3, math.pi / 3, -0.1 * 2 * math.pi / 3, -0.1 * 2 * math.pi / 3 + 0.1 * 0.1]))
+  with pytest.raises(AssertionError):
+    pen.piecewise_circle_penalty(jx, jy, jx, jy, jx, inside_slope=-1.0)
+  with pytest.raises(AssertionError):
+    pen.piecewise_joint_limit_penalty(theta, theta, theta, outside_slope=-1.0)
+
+
+def test_penalty_dropins_bit_exact_with_reference_golden(cuda_device):
+  import kinematics.penalties as pen
+  g = golden_npz("penalties.npz")
+  dev = cuda_device
+  for i, (a_in, a_out) in enumerate(g["circle_slopes"]):
+    x = torch.from_numpy(g["jx"]).to(dev).requires_grad_(True)
+    y = torch.from_numpy(g["jy"]).to(dev).requires_grad_(True)
+    p = pen.piecewise_circle_penalty(x, y, torch.from_numpy(g["ox"]).to(dev), torch.from_numpy(g["oy"]).to(dev),
+                                     torch.from_numpy(g["radius"]).to(dev), float(a_in), float(a_out))
+    p.sum().backward()
+    assert np.array_equal(p.detach().cpu().numpy(), g["circle_%d" % i]), "circle values must be bit-identical"
+    close(x.grad.cpu().numpy(), g["circle_%d_djx_f64" % i], rtol=2e-6)
+    close(y.grad.cpu().numpy(), g["circle_%d_djy_f64" % i], rtol=2e-6)
+    # tie rows (first three: exactly on the circle) carry the averaged slope like torch
+    np.testing.assert_allclose(x.grad.cpu().numpy()[:2], g["circle_%d_djx" % i][:2], rtol=1e-6, atol=1e-7)
+  for li, (lo, hi) in enumerate(g["jl_limits"]):
+    for si, (a_in, a_out) in enumerate(g["jl_slopes"]):
+      t = torch.from_numpy(g["jl_theta_%d" % li]).to(dev).requires_grad_(True)
+      p = pen.piecewise_joint_limit_penalty(t, torch.Tensor([lo]).to(dev), torch.Tensor([hi]).to(dev), float(a_in), float(a_out))
+      p.sum().backward()
+      assert np.array_equal(p.detach().cpu().numpy(), g["jl_%d_%d" % (li, si)]), "joint-limit values must be bit-identical"
+      assert np.array_equal(t.grad.cpu().numpy(), g["jl_%d_%d_dtheta" % (li, si)]), "joint-limit gradient (incl. ties) must match torch"
+
+
+def test_circle_centre_gradient_is_zero_not_nan(cuda_device):
+  import kinematics.penalties as pen
+  x = torch.tensor([0.5], device=cuda_device, requires_grad=True)
+  y = torch.tensor([0.5], device=cuda_device, requires_grad=True)
+  c = torch.tensor([0.5], device=cuda_device)
+  p = pen.piecewise_circle_penalty(x, y, c, c, torch.tensor([0.25], device=cuda_device), 1.0, 0.1)
+  p.sum().backward()
+  assert p.item() == 0.25 and x.grad.item() == 0.0 and y.grad.item() == 0.0
+
+
+def test_penalty_dropins_accept_trainer_style_views(cuda_device):
+  """Column slices of (B,3)/(B,4,4) tensors and expand()-ed limits, exactly what scripts/trainer.py:201-204,:233-238 pass."""
+  import kinematics.penalties as pen
+  torch.manual_seed(5)
+  B = 77
+  q = torch.randn(B, 3)
+  ob = torch.rand(B, 4, 4)
+  th = torch.randn(B, 3) * 2
+  lim = torch.Tensor([-2.094395, 2.094395]).unsqueeze(0).expand(B, -1)
+  ref_c = O.circle_penalty(q[:, 0], q[:, 1], ob[:, 2, 0], ob[:, 2, 1], ob[:, 2, 2], 1.0, 0.005)
+  ref_j = O.joint_limit_penalty(th[:, 1], lim[:, 0], lim[:, 1], 0.005, 1.0)
+  qg, obg, thg, limg = q.to(cuda_device).requires_grad_(True), ob.to(cuda_device), th.to(cuda_device).requires_grad_(True), lim.to(cuda_device)
+  got_c = pen.piecewise_circle_penalty(qg[:, 0], qg[:, 1], obg[:, 2, 0], obg[:, 2, 1], obg[:, 2, 2], 1.0, 0.005)
+  got_j = pen.piecewise_joint_limit_penalty(thg[:, 1], limg[:, 0], limg[:, 1], 0.005, 1.0)
+  assert np.array_equal(got_c.detach().cpu().numpy(), ref_c.numpy())
+  assert np.array_equal(got_j.detach().cpu().numpy(), ref_j.numpy())
+  (got_c.sum() + got_j.sum()).backward()
+  assert qg.grad.shape == (B, 3) and float(qg.grad[:, 2].abs().sum()) == 0.0
+  assert thg.grad.shape == (B, 3) and float(thg.grad[:, 0].abs().sum()) == 0.0
+  # 2-D broadcasting (points x obstacles)
+  got2 = pen.piecewise_circle_penalty(qg[:, 0:1], qg[:, 1:2], obg[0, :, 0], obg[0, :, 1], obg[0, :, 2], 1.0, 0.1)
+  ref2 = O.circle_penalty(q[:, 0:1], q[:, 1:2], ob[0, :, 0], ob[0, :, 1], ob[0, :, 2], 1.0, 0.1)
+  assert got2.shape == (B, 4) and np.array_equal(got2.detach().cpu().numpy(), ref2.numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# level (ii): the fused Lagrangian
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_fused_matches_real_trainer_golden(name, layout, cuda_device, monkeypatch):
+  """Outputs of the unmodified IkLagrangeDualTrainer.process_batch + backward (tests/golden/make_golden.py)."""
+  g = golden_npz("process_batch_%s.npz" % name)
+  spec, ospec = specs_for(name, float(g["good_slope"]), float(g["bad_slope"]))
+  theta, q_des, obst = (torch.from_numpy(g[k]) for k in ("theta", "q_ee_desired", "dynamic_obstacles"))
+  for tag in ("shipped", "ramp"):
+    lam = g["lam_" + tag]
+    _, abs_sums, dth64, kink, _ = oracle_truth(ospec, theta, q_des, obst, lam)
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(cuda_device)):          # by value / read on device
+      viol, loss, dth, kname = run_layout(layout, spec, theta, q_des, obst, weights, True, monkeypatch)
+      assert layout in kname, kname
+      assert np.all(np.abs(viol - g["viol_" + tag]) <= RTOL * abs_sums + 1e-30), (viol, g["viol_" + tag])
+      close(loss, g["loss_" + tag], scale=float(np.abs(lam * abs_sums).sum()))
+      close(dth[~kink], g["dtheta_" + tag][~kink], scale=np.abs(g["dtheta_" + tag]).max())
+      close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
+    viol_f, loss_f, _, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
+    assert np.array_equal(viol_f, viol), "forward-only and fused fwd+bwd launches must give identical sums"
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("B", [8, 1000, 1 << 16])
+def test_fused_vs_oracle_seeded_batches(B, layout, cuda_device, monkeypatch):
+  from ikl import synthetic
+  for name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static", "cfg_no_constraints"):
+    spec, ospec = specs_for(name)
+    theta, q_des, obst = synthetic.make_batch(B, seed=B + 7)
+    lam = (1.0 + 0.25 * np.arange(spec.num_constraints)).astype(np.float32)
+    sums64, abs_sums, dth64, kink, _ = oracle_truth(ospec, theta, q_des, obst, lam)
+    ref32 = O.lagrangian_with_grad(theta, q_des, torch.from_numpy(lam), ospec, obst if ospec.dynamic else None)
+    viol, loss, dth, kname = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums), name
+    assert np.all(np.abs(viol - ref32["constraint_violations"].numpy()) <= RTOL * abs_sums), name
+    close(loss, float((lam * sums64).sum()), scale=float((lam * abs_sums).sum()))
+    assert kink.mean() < 1e-3
+    close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
+    close(dth[~kink], ref32["dtheta"].numpy()[~kink], scale=np.abs(dth64).max())
+
+
+def test_fused_vs_oracle_one_million(cuda_device, monkeypatch):
+  from ikl import synthetic
+  B = 1 << 20
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  theta, q_des, obst = synthetic.make_batch(B, seed=99)
+  lam = np.asarray(synthetic.SHIPPED_LAMBDA_OBS4_DYN, dtype=np.float32)
+  sums64, abs_sums, dth64, kink, _ = oracle_truth(ospec, theta, q_des, obst, lam)
+  for layout in ("rows", "planes"):
+    viol, loss, dth, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums)
+    assert kink.mean() < 1e-3
+    close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
+
+
+@pytest.mark.parametrize("B", [0, 1, 2, 3, 5, 255, 257, 1023])
+def test_ragged_and_empty_batches(B, cuda_device, monkeypatch):
+  from ikl import synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  theta, q_des, obst = synthetic.make_batch(max(B, 1), seed=B)
+  theta, q_des, obst = theta[:B], q_des[:B], obst[:B]
+  lam = np.linspace(0.5, 2.0, 16).astype(np.float32)
+  layouts = ("rows", "strided") + (("planes",) if B % 4 == 0 else ())
+  for layout in layouts:
+    viol, loss, dth, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    if B == 0:
+      assert np.all(viol == 0) and loss == 0.0 and dth.shape == (0, 3)
+      continue
+    sums64, abs_sums, dth64, kink, _ = oracle_truth(ospec, theta, q_des, obst, lam)
+    assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums)
+    close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
+
+
+def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
+  """theta exactly at a limit / at mid-range, a tip exactly on a circle, a tip exactly on a centre."""
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  lim = float(np.float32(2.094395))
+  theta = torch.tensor([[0.0, 0.0, 0.0],            # tips (1,0),(2,0),(3,0); joints at mid-range
+                        [lim, -lim, 0.0],           # joints exactly at the limits (|u| == h)
+                        [0.0, 0.0, 0.0]])
+  q_des = torch.tensor([[3.0, 0.0, 0.0], [1.0, 1.0, 0.0], [2.5, 0.5, 0.0]])
+  obst = torch.zeros(3, 4, 4)
+  obst[:, :, 0] = 10.0                               # park unused obstacles far away
+  obst[:, :, 2] = 0.4
+  obst[0, 0, :3] = torch.tensor([2.0, 0.4, 0.4])     # tip 2 exactly ON the circle (d == r): averaged slope
+  obst[2, 1, :3] = torch.tensor([1.0, 0.0, 0.4])     # tip 1 exactly on the CENTRE: torch NaN, here 0 direction
+  lam = np.ones(16, dtype=np.float32)
+  ref = O.lagrangian_with_grad(theta, q_des, torch.from_numpy(lam), ospec, obst)
+  assert torch.isnan(ref["dtheta"][2]).any(), "reference behaviour (NaN at a circle centre) changed?"
+  _, dth64 = O.lagrangian_grad_closed_form(theta.numpy(), q_des.numpy(), lam, ospec, obst.numpy())
+  for layout in ("rows", "strided"):
+    viol, loss, dth, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    assert np.isfinite(dth).all()
+    close(viol, ref["constraint_violations"].numpy(), scale=10.0)
+    close(dth[:2], ref["dtheta"].numpy()[:2], scale=np.abs(dth64).max(), rtol=2e-6)   # ties reproduced exactly like torch
+    close(dth[2], dth64[2], scale=np.abs(dth64).max(), rtol=2e-6)
+
+
+def test_autograd_function_and_general_upstream_gradients(cuda_device):
+  from ikl import fused, synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  B = 4096
+  theta, q_des, obst = synthetic.make_batch(B, seed=21)
+  lam = torch.linspace(0.2, 3.0, 16)
+  gv = torch.randn(16)
+  th_ref = theta.double().requires_grad_(True)
+  out = O.lagrangian(th_ref, q_des.double(), lam.double(), ospec, obst.double(), per_sample=True)
+  (2.5 * out["lagrange_loss"] + (gv.double() * out["constraint_violations"]).sum()).backward()
+  kink = (out["per_sample_terms"].detach().numpy()[:, 1:].__abs__() < 1e-6).any(axis=1)
+  dev = cuda_device
+  th = theta.to(dev).requires_grad_(True)
+  viol, loss = fused.ik_lagrangian(th, q_des.to(dev), obst.to(dev), lam.to(dev), spec)
+  (2.5 * loss + (gv.to(dev) * viol).sum()).backward()
+  close(th.grad.cpu().numpy()[~kink], th_ref.grad.numpy()[~kink], scale=th_ref.grad.abs().max().item())
+  # plain loss.backward(), host-side multipliers (the training-loop configuration)
+  th2 = theta.to(dev).requires_grad_(True)
+  viol2, loss2 = fused.ik_lagrangian(th2, q_des.to(dev), obst.to(dev), lam.to(dev), spec, lam_host=lam.tolist())
+  loss2.backward()
+  th_ref2 = theta.double().requires_grad_(True)
+  O.lagrangian(th_ref2, q_des.double(), lam.double(), ospec, obst.double())["lagrange_loss"].backward()
+  close(th2.grad.cpu().numpy()[~kink], th_ref2.grad.numpy()[~kink], scale=th_ref2.grad.abs().max().item())
+  # no grad requested -> forward-only kernel, same numbers
+  with torch.no_grad():
+    viol3, loss3 = fused.ik_lagrangian(theta.to(dev), q_des.to(dev), obst.to(dev), lam.to(dev), spec)
+  assert torch.equal(viol3, viol2) and not viol3.requires_grad
+
+
+def test_side_outputs_q_ee_and_position_error(cuda_device):
+  from ikl import fused, synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_1obs_static")
+  theta, q_des, obst = synthetic.make_batch(1000, seed=4)
+  ref = O.lagrangian(theta.double(), q_des.double(), torch.ones(7).double(), ospec)
+  out = fused.lagrangian_forward(spec, theta.cuda(), q_des.cuda(), None, [1.0] * 7, want_q_ee=True, want_err_sq=True)
+  close(out["q_ee_actual"].cpu().numpy(), ref["q_ee_actual"].numpy(), scale=3.0)
+  close(out["position_err_sq"].cpu().numpy(), ref["position_err_sq"].numpy())
+
+
+def test_error_behaviour(cuda_device):
+  from ikl import fused
+  spec, _ = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  th = torch.zeros(8, 3, device=cuda_device)
+  qd = torch.zeros(8, 3, device=cuda_device)
+  with pytest.raises(ValueError):
+    fused.lagrangian_forward(spec, th, qd, None, [1.0] * 16)                 # dynamic config without obstacles (trainer.py:211)
+  with pytest.raises(ValueError):
+    fused.lagrangian_forward(spec, th, qd, torch.zeros(8, 4, 4, device=cuda_device), [1.0] * 4)   # wrong K
+  with pytest.raises(RuntimeError):
+    fused.lagrangian_forward(spec, th.cpu(), qd.cpu(), torch.zeros(8, 4, 4), [1.0] * 16)          # CPU tensors: no fallback
+  with pytest.raises(TypeError):
+    fused.lagrangian_forward(spec, th.double(), qd, torch.zeros(8, 4, 4, device=cuda_device), [1.0] * 16)
+  with pytest.raises(ValueError):
+    fused.lagrangian_forward(spec, torch.zeros(8, 2, device=cuda_device), qd, torch.zeros(8, 4, 4, device=cuda_device), [1.0] * 16)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# dual ascent
+# ------------------------------------------------------------------------------------------------------------
+def test_dual_update_and_accumulation_match_oracle(cuda_device):
+  from ikl import fused, synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  dev = cuda_device
+  lam = torch.tensor(synthetic.SHIPPED_LAMBDA_OBS4_DYN)
+  theta, q_des, obst = synthetic.make_batch(4000, seed=8)
+  # the reference stacks per-batch K-vectors over the validation loader (batch 8 -> 500 batches) and sums them
+  per_batch = []
+  accum = torch.zeros(16, dtype=torch.float64, device=dev)
+  for s in range(0, 4000, 500):
+    sl = slice(s, s + 500)
+    per_batch.append(O.lagrangian(theta[sl], q_des[sl], lam, ospec, obst[sl])["constraint_violations"])
+    fused.lagrangian_forward(spec, theta[sl].to(dev), q_des[sl].to(dev), obst[sl].to(dev), lam.to(dev), viol_accum=accum)
+  want = O.dual_update(lam, torch.stack(per_batch), 1e-4)
+  got = fused.dual_update(lam.to(dev), accum, 1e-4)
+  close(got.cpu().numpy(), want.numpy(), scale=float(want.abs().max()))
+  assert bool((got >= 0).all())
+  # clamp semantics on a hand vector (trainer.py:280-284), float32 sums
+  got2 = fused.dual_update(torch.tensor([1.0, 0.0, 0.5], device=dev), torch.tensor([20.0, -10.0, -60.0], device=dev), 1e-2)
+  torch.testing.assert_close(got2.cpu(), torch.tensor([1.2, 0.0, 0.0]))
+
+
+def test_lambda_trajectory_from_identical_theta(cuda_device):
+  """N dual steps driven by the same theta sequence on both sides: lambda trajectories must agree to 1e-5."""
+  from ikl import fused, synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  dev = cuda_device
+  lam_ref = torch.ones(16)
+  lam_gpu = torch.ones(16, device=dev)
+  for step in range(12):
+    theta, q_des, obst = synthetic.make_batch(2048, seed=100 + step)
+    v = O.lagrangian(theta, q_des, lam_ref, ospec, obst)["constraint_violations"]
+    lam_ref = O.dual_update(lam_ref, v.unsqueeze(0), 1e-3)
+    out = fused.lagrangian_forward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam_gpu)
+    lam_gpu = fused.dual_update(lam_gpu, out["constraint_violations"].contiguous(), 1e-3)
+    close(lam_gpu.cpu().numpy(), lam_ref.numpy(), scale=float(lam_ref.abs().max()))
+  assert float(lam_ref.max()) > 1.5 and float(lam_ref.min()) == 0.0     # the trajectory actually moved and clamped
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full benchmark size (2^24): size-independent properties + oracle spot checks
+# ------------------------------------------------------------------------------------------------------------
+def test_full_size_properties(cuda_device, monkeypatch):
+  from ikl import fused, synthetic
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  B = 1 << 24
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  dev = cuda_device
+  theta, q_des, obst = synthetic.make_batch(B, seed=1, device="cuda:0")
+  lam1 = torch.tensor(synthetic.SHIPPED_LAMBDA_OBS4_DYN)
+  lam2 = torch.linspace(0.1, 1.6, 16)
+  v1, l1, d1 = fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam1.tolist())
+  v2, l2, d2 = fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam2.tolist())
+  v12, l12, d12 = fused.lagrangian_forward_backward(spec, theta, q_des, obst, (lam1 + lam2).tolist())
+  # (a) the sums do not depend on the weights; the loss and the gradient are linear in them
+  assert torch.equal(v1, v2) and torch.equal(v1, v12)
+  scale = float(d12.abs().max())
+  assert float((d1 + d2 - d12).abs().max()) <= 4e-6 * scale
+  assert abs(float(l1 + l2 - l12)) <= 1e-5 * float((lam1 + lam2).to(dev) @ v1.abs())
+  # (b) a sum over the batch equals the sum of the sums over its quarters (and determinism: same launch twice)
+  parts = sum(fused.lagrangian_forward(spec, theta[s:s + B // 4], q_des[s:s + B // 4], obst[s:s + B // 4], lam1.tolist())
+              ["constraint_violations"].double() for s in range(0, B, B // 4))
+  abs_bound = 1e-5 * (B * 3.0)          # every |term| <= ~3 (slopes <= 1, distances <= ~6)
+  assert float((parts - v1.double()).abs().max()) <= 1e-5 * float(v1.abs().max()) + 1e-9 * abs_bound
+  v1b, _, d1b = fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam1.tolist())
+  assert torch.equal(v1b, v1) and torch.equal(d1b, d1), "launches are deterministic"
+  # (c) layout independence: planes give the same per-sample gradient bits and the same sums to round-off
+  thp, tgp, obp = synthetic.to_planes(theta, q_des, obst)
+  vp, lp, dp = fused.lagrangian_forward_backward(spec, thp, tgp, obp, lam1.tolist())
+  assert torch.equal(dp.contiguous(), d1.contiguous()) if dp.shape == d1.shape else False
+  assert float((vp - v1).abs().max()) <= 1e-6 * float(v1.abs().max())
+  # (d) oracle spot checks on slices of the big batch
+  for s in (0, 5_000_000, B - 4096):
+    sl = slice(s, s + 4096)
+    th, qd, ob = theta[sl].cpu(), q_des[sl].cpu(), obst[sl].cpu()
+    _, _, dth64, kink, _ = oracle_truth(ospec, th, qd, ob, lam1.numpy())
+    close(d1[sl].cpu().numpy()[~kink], dth64[~kink], scale=np.abs(dth64).max())
+  # (e) whole-batch sums against a float64 oracle evaluated in chunks on the host
+  tot = np.zeros(16)
+  tot_abs = np.zeros(16)
+  for s in range(0, B, 1 << 22):
+    sl = slice(s, s + (1 << 22))
+    o = O.lagrangian(theta[sl].cpu().double(), q_des[sl].cpu().double(), lam1.double(), ospec, obst[sl].cpu().double(), per_sample=True)
+    tot += o["constraint_violations"].numpy()
+    tot_abs += o["per_sample_terms"].abs().sum(dim=0).numpy()
+  assert np.all(np.abs(v1.cpu().numpy() - tot) <= RTOL * tot_abs)
