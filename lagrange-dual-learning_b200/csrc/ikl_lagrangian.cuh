@@ -21,7 +21,7 @@ namespace ikl {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kFlushEvery = 8;      // outer iterations between fp32 -> fp64 accumulator flushes
+constexpr int kFlushSamples = 64;   // samples a thread adds in fp32 before flushing into its fp64 slot in shared memory
 constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce
 
 #ifndef IKL_PLANES_VEC
@@ -79,15 +79,33 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
 }
 
 // ---- reduction tail ----------------------------------------------------------------------------------
-template <int K, bool WDEV>
-__device__ __forceinline__ void finalize_sums(const LagrangianParams& p, double (&dacc)[K]) {
+// Second-level accumulators: one fp64 slot per (constraint, thread) in shared memory, so the hot loop only
+// carries the K fp32 running sums in registers.
+template <int K>
+struct SharedAcc {
+  double v[K][kThreads];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i][threadIdx.x] = 0.0;
+  }
+  __device__ __forceinline__ void flush(float (&acc)[K]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      v[i][threadIdx.x] += (double)acc[i];
+      acc[i] = 0.f;
+    }
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void finalize_sums(const LagrangianParams& p, SharedAcc<K>& sacc) {
   __shared__ double s_red[kWarps][kMaxK];
   __shared__ double s_fin[kFinalParts][kMaxK];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    double v = dacc[i];
+    double v = sacc.v[i][tid];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane == 0) s_red[warp][i] = v;
@@ -204,7 +222,7 @@ __device__ __forceinline__ void store_sample(const LagrangianParams& p, long lon
 }
 
 template <class C, class W>
-__device__ __forceinline__ void run_scalar_layout(const LagrangianParams& p, const W& w, double (&dacc)[C::K]) {
+__device__ __forceinline__ void run_scalar_layout(const LagrangianParams& p, const W& w, SharedAcc<C::K>& sacc) {
   constexpr int U = IKL_ROWS_UNROLL;
   const long long B = p.batch;
   const long long step = (long long)gridDim.x * (kThreads * U);
@@ -229,14 +247,12 @@ __device__ __forceinline__ void run_scalar_layout(const LagrangianParams& p, con
         store_sample<C>(p, b, dth, ee, tx[uu], ty[uu]);
       }
     }
-    if (++since_flush == kFlushEvery) {
+    if (++since_flush == kFlushSamples / U) {
       since_flush = 0;
-#pragma unroll
-      for (int i = 0; i < C::K; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
+      sacc.flush(acc);
     }
   }
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) dacc[i] += (double)acc[i];
+  sacc.flush(acc);
 }
 
 // ---- planes layout: kVec consecutive samples per thread, 16-byte (or 8-byte) accesses ------------------------
@@ -259,7 +275,7 @@ template <> struct VecIO<2> {
 };
 
 template <class C, class W>
-__device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w, double (&dacc)[C::K]) {
+__device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w, SharedAcc<C::K>& sacc) {
   constexpr int V = IKL_PLANES_VEC;
   using IO = VecIO<V>;
   const long long nvec = p.batch / V;             // the API guarantees batch % V == 0 for this layout
@@ -327,29 +343,26 @@ __device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w
         }
       }
     }
-    if (++since_flush == kFlushEvery) {
+    if (++since_flush == kFlushSamples / V) {
       since_flush = 0;
-#pragma unroll
-      for (int i = 0; i < C::K; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
+      sacc.flush(acc);
     }
   }
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) dacc[i] += (double)acc[i];
+  sacc.flush(acc);
 }
 
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
-  double dacc[C::K];
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) dacc[i] = 0.0;
+  __shared__ SharedAcc<C::K> sacc;
+  sacc.clear();
   if (C::MODE == kGradDevW) {
     const DeviceWeights<C::K> w(p.u, p.w_dev);
-    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, dacc); else run_scalar_layout<C>(p, w, dacc);
+    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, sacc); else run_scalar_layout<C>(p, w, sacc);
   } else {
     const HostWeights w(p.u, nullptr);
-    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, dacc); else run_scalar_layout<C>(p, w, dacc);
+    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, sacc); else run_scalar_layout<C>(p, w, sacc);
   }
-  finalize_sums<C::K, C::MODE == kGradDevW>(p, dacc);
+  finalize_sums<C::K>(p, sacc);
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------------------

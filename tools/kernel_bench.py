@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Kernel-only timing table for the fused Lagrangian kernels (CUDA events, back-to-back launches, inputs >> L2).
+
+  python tools/kernel_bench.py [--batch-log2 24] [--iters 30] [--libs a.so,b.so]   # libs: variant builds to compare
+
+Each lib is measured in a fresh subprocess (IKL_LIB) so variants do not share state.  Prints one JSON line per row.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "lagrange-dual-learning_b200")
+for p in (ROOT, PKG):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+
+def measure(args):
+  import torch
+  from ikl import ConstraintSpec, standard_config, fused, synthetic, _cabi
+  dev = torch.device("cuda:0")
+  B = 1 << args.batch_log2
+  theta, q_des, obst = synthetic.make_batch(B, seed=0, device="cuda:0")
+  planes = synthetic.to_planes(theta, q_des, obst)
+  rows = (theta, q_des, obst)
+  peak = 6548.8
+  try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+  except Exception:
+    pass
+  cases = [("cfg_joint_limits_and_4obs_dynamic", 80, 68), ("cfg_joint_limits_and_4obs_static", 32, 20),
+           ("cfg_joint_limits", 32, 20), ("cfg_no_constraints", 32, 20)]
+  if args.quick:
+    cases = cases[:1]
+  for cfg_name, bytes_fb, bytes_f in cases:
+    spec = ConstraintSpec.from_config(standard_config(cfg_name), 3, 0.005, 1.0)
+    K = spec.num_constraints
+    lam = [1.0 + 0.1 * i for i in range(K)]
+    lam_dev = torch.tensor(lam, device=dev)
+    for lname, (th, tg, ob) in (("planes", planes), ("rows", rows)):
+      dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
+      for mode in ("fwdbwd_hostw", "fwdbwd_devw", "fwd"):
+        if args.quick and mode == "fwdbwd_devw":
+          continue
+        def call():
+          if mode == "fwd":
+            return fused.lagrangian_forward(spec, th, tg, ob if spec.dynamic else None, lam)
+          return fused.lagrangian_forward_backward(spec, th, tg, ob if spec.dynamic else None, lam if mode == "fwdbwd_hostw" else lam_dev, dtheta=dth)
+        for _ in range(3):
+          call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        tot = 0.0
+        for rep in range(3):
+          e0.record()
+          for _ in range(args.iters):
+            call()
+          e1.record()
+          torch.cuda.synchronize()
+          ms = e0.elapsed_time(e1) / args.iters
+          best = min(best, ms)
+          tot += ms
+        nbytes = bytes_f if mode == "fwd" else bytes_fb
+        print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "config": cfg_name, "layout": lname, "mode": mode,
+                          "kernel": _cabi.last_kernel_name(), "ms_mean": round(tot / 3, 4), "ms_best": round(best, 4),
+                          "gsamples_per_s": round(B / best / 1e6, 2), "algo_GBps": round(nbytes * B / best / 1e6, 1),
+                          "frac_of_hbm_peak": round(nbytes * B / best / 1e6 / peak, 4)}), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--batch-log2", type=int, default=24)
+  ap.add_argument("--iters", type=int, default=30)
+  ap.add_argument("--libs", default="")
+  ap.add_argument("--quick", action="store_true")
+  ap.add_argument("--child", action="store_true")
+  args = ap.parse_args()
+  if args.child or not args.libs:
+    measure(args)
+    return
+  for lib in args.libs.split(","):
+    env = dict(os.environ, IKL_LIB=os.path.join(PKG, "lib", lib) if not os.path.isabs(lib) else lib)
+    cmd = [sys.executable, os.path.abspath(__file__), "--child", "--batch-log2", str(args.batch_log2), "--iters", str(args.iters)]
+    if args.quick:
+      cmd.append("--quick")
+    subprocess.run(cmd, env=env, check=False)
+
+
+if __name__ == "__main__":
+  main()
