@@ -39,7 +39,7 @@ def test_abi_version_and_housekeeping():
   assert lib.ikl_launch_count() >= 0
 
 
-@pytest.mark.parametrize("name,K", zip(STANDARD_CONFIGS, (1, 4, 7, 16, 16)))
+@pytest.mark.parametrize("name,K", list(zip(STANDARD_CONFIGS, (1, 4, 7, 16, 16))))
 def test_constraint_count_matches_shipped_multiplier_sizes(name, K):
   spec = ConstraintSpec.from_config(standard_config(name), 3, 0.005, 1.0)
   assert spec.num_constraints == K

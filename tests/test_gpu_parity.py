@@ -152,19 +152,32 @@ def test_reference_known_answers_through_dropin(cuda_device):
 
 
 def test_penalty_dropins_bit_exact_with_reference_golden(cuda_device):
+  """Joint-limit values and gradients are bit-identical to the reference's torch-CPU results.  Circle values are
+  bit-identical to the IEEE evaluation of the reference's formula (numpy float32: every op correctly rounded);
+  torch's own vectorised CPU sqrt is NOT correctly rounded on every input (2 of the 390 golden points differ from
+  IEEE by 1 ulp on the AVX512 build that produced the fixtures), so against the golden values the bound is 1 ulp of d."""
   import kinematics.penalties as pen
   g = golden_npz("penalties.npz")
   dev = cuda_device
+  f = np.float32
+  jx, jy, ox, oy, rad = (g[k].astype(f) for k in ("jx", "jy", "ox", "oy", "radius"))
+  dx, dy = jx - ox, jy - oy
+  d_ieee = np.sqrt(dx * dx + dy * dy)
   for i, (a_in, a_out) in enumerate(g["circle_slopes"]):
     x = torch.from_numpy(g["jx"]).to(dev).requires_grad_(True)
     y = torch.from_numpy(g["jy"]).to(dev).requires_grad_(True)
     p = pen.piecewise_circle_penalty(x, y, torch.from_numpy(g["ox"]).to(dev), torch.from_numpy(g["oy"]).to(dev),
                                      torch.from_numpy(g["radius"]).to(dev), float(a_in), float(a_out))
     p.sum().backward()
-    assert np.array_equal(p.detach().cpu().numpy(), g["circle_%d" % i]), "circle values must be bit-identical"
+    got = p.detach().cpu().numpy()
+    ieee = np.maximum(f(-a_in) * (d_ieee - rad), f(-a_out) * (d_ieee - rad))
+    assert np.array_equal(got, ieee), "circle values must equal the correctly-rounded evaluation bit for bit"
+    ref = g["circle_%d" % i]
+    assert np.all(np.abs(got - ref) <= max(a_in, a_out) * np.spacing(d_ieee) * 1.01), "within 1 ulp(d) of torch's CPU result"
+    assert (got != ref).mean() < 0.02
     close(x.grad.cpu().numpy(), g["circle_%d_djx_f64" % i], rtol=2e-6)
     close(y.grad.cpu().numpy(), g["circle_%d_djy_f64" % i], rtol=2e-6)
-    # tie rows (first three: exactly on the circle) carry the averaged slope like torch
+    # tie rows (first two: exactly on the circle) carry the averaged slope like torch
     np.testing.assert_allclose(x.grad.cpu().numpy()[:2], g["circle_%d_djx" % i][:2], rtol=1e-6, atol=1e-7)
   for li, (lo, hi) in enumerate(g["jl_limits"]):
     for si, (a_in, a_out) in enumerate(g["jl_slopes"]):
@@ -199,7 +212,7 @@ def test_penalty_dropins_accept_trainer_style_views(cuda_device):
   qg, obg, thg, limg = q.to(cuda_device).requires_grad_(True), ob.to(cuda_device), th.to(cuda_device).requires_grad_(True), lim.to(cuda_device)
   got_c = pen.piecewise_circle_penalty(qg[:, 0], qg[:, 1], obg[:, 2, 0], obg[:, 2, 1], obg[:, 2, 2], 1.0, 0.005)
   got_j = pen.piecewise_joint_limit_penalty(thg[:, 1], limg[:, 0], limg[:, 1], 0.005, 1.0)
-  assert np.array_equal(got_c.detach().cpu().numpy(), ref_c.numpy())
+  np.testing.assert_allclose(got_c.detach().cpu().numpy(), ref_c.numpy(), rtol=0, atol=3e-7)     # torch CPU sqrt: see above
   assert np.array_equal(got_j.detach().cpu().numpy(), ref_j.numpy())
   (got_c.sum() + got_j.sum()).backward()
   assert qg.grad.shape == (B, 3) and float(qg.grad[:, 2].abs().sum()) == 0.0
@@ -207,7 +220,8 @@ def test_penalty_dropins_accept_trainer_style_views(cuda_device):
   # 2-D broadcasting (points x obstacles)
   got2 = pen.piecewise_circle_penalty(qg[:, 0:1], qg[:, 1:2], obg[0, :, 0], obg[0, :, 1], obg[0, :, 2], 1.0, 0.1)
   ref2 = O.circle_penalty(q[:, 0:1], q[:, 1:2], ob[0, :, 0], ob[0, :, 1], ob[0, :, 2], 1.0, 0.1)
-  assert got2.shape == (B, 4) and np.array_equal(got2.detach().cpu().numpy(), ref2.numpy())
+  assert got2.shape == (B, 4)
+  np.testing.assert_allclose(got2.detach().cpu().numpy(), ref2.numpy(), rtol=0, atol=3e-7)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -401,9 +415,9 @@ def test_lambda_trajectory_from_identical_theta(cuda_device):
   for step in range(12):
     theta, q_des, obst = synthetic.make_batch(2048, seed=100 + step)
     v = O.lagrangian(theta, q_des, lam_ref, ospec, obst)["constraint_violations"]
-    lam_ref = O.dual_update(lam_ref, v.unsqueeze(0), 1e-3)
+    lam_ref = O.dual_update(lam_ref, v.unsqueeze(0), 1e-2)
     out = fused.lagrangian_forward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam_gpu)
-    lam_gpu = fused.dual_update(lam_gpu, out["constraint_violations"].contiguous(), 1e-3)
+    lam_gpu = fused.dual_update(lam_gpu, out["constraint_violations"].contiguous(), 1e-2)
     close(lam_gpu.cpu().numpy(), lam_ref.numpy(), scale=float(lam_ref.abs().max()))
   assert float(lam_ref.max()) > 1.5 and float(lam_ref.min()) == 0.0     # the trajectory actually moved and clamped
 
@@ -438,7 +452,7 @@ def test_full_size_properties(cuda_device, monkeypatch):
   # (c) layout independence: planes give the same per-sample gradient bits and the same sums to round-off
   thp, tgp, obp = synthetic.to_planes(theta, q_des, obst)
   vp, lp, dp = fused.lagrangian_forward_backward(spec, thp, tgp, obp, lam1.tolist())
-  assert torch.equal(dp.contiguous(), d1.contiguous()) if dp.shape == d1.shape else False
+  assert torch.equal(dp.contiguous(), d1.contiguous())
   assert float((vp - v1).abs().max()) <= 1e-6 * float(v1.abs().max())
   # (d) oracle spot checks on slices of the big batch
   for s in (0, 5_000_000, B - 4096):
@@ -449,8 +463,8 @@ def test_full_size_properties(cuda_device, monkeypatch):
   # (e) whole-batch sums against a float64 oracle evaluated in chunks on the host
   tot = np.zeros(16)
   tot_abs = np.zeros(16)
-  for s in range(0, B, 1 << 22):
-    sl = slice(s, s + (1 << 22))
+  for s in range(0, B, 1 << 21):
+    sl = slice(s, s + (1 << 21))
     o = O.lagrangian(theta[sl].cpu().double(), q_des[sl].cpu().double(), lam1.double(), ospec, obst[sl].cpu().double(), per_sample=True)
     tot += o["constraint_violations"].numpy()
     tot_abs += o["per_sample_terms"].abs().sum(dim=0).numpy()
