@@ -39,6 +39,7 @@ int sm_count() {
 namespace {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 int forced_layout() {
   const char* e = getenv("IKL_FORCE_LAYOUT");
@@ -99,6 +100,22 @@ void fill_uniforms(const IklSpec* spec, const float* w_host, Uniforms& u) {
   }
 }
 
+void fill_packed_uniforms(const IklSpec* spec, const Uniforms& u, PackedUniforms& pu) {
+  memset(&pu, 0, sizeof(pu));
+  auto dup = [](float v) { return make_float2(v, v); };
+  const float half = 0.5f * fabsf(spec->limit_hi - spec->limit_lo);
+  const float smin = fminf(u.jl_in, u.jl_out), smax = fmaxf(u.jl_in, u.jl_out);
+  pu.jl_mid = dup(u.jl_mid);
+  pu.jl_half = dup(half);
+  pu.jl_smin = dup(smin);
+  pu.jl_sdiff = dup(smax - smin);
+  pu.ob_nlo = dup(-u.ob_lo);
+  pu.ob_ndiff = dup(u.ob_lo - u.ob_hi);
+  for (int o = 0; o < kMaxObst; ++o)
+    for (int c = 0; c < 3; ++c) pu.stat_ob[o][c] = dup(u.stat_ob[o][c]);
+  for (int i = 0; i < kMaxK; ++i) pu.lam[i] = dup(u.w[i]);
+}
+
 bool unit_links(const IklSpec* spec) {
   for (int m = 0; m < spec->num_links; ++m)
     if (spec->link_length[m] != 1.0f) return false;
@@ -114,11 +131,11 @@ int detect_layout(const IklSpec* spec, const IklBatch* in, bool grad, const floa
                     (!dyn || (in->obst_sc == 1 && in->obst_so == 4 && in->obst_sb == 4 * kMaxObst && aligned16(in->obstacles))) &&
                     (!grad || (dt_sj == 1 && dt_sb == J));
   if (rows) return kRows;
-  constexpr int V = IKL_PLANES_VEC;
-  const bool planes = in->theta_sb == 1 && in->target_sb == 1 && in->batch % V == 0 && aligned16(in->theta) && in->theta_sj % 4 == 0 &&
-                      aligned16(in->target) && in->target_sc % 4 == 0 &&
-                      (!dyn || (in->obst_sb == 1 && aligned16(in->obstacles) && in->obst_so % 4 == 0 && in->obst_sc % 4 == 0)) &&
-                      (!grad || (dt_sb == 1 && dt_sj % 4 == 0 && aligned16(dtheta)));
+  // planes: every plane is read two samples at a time with 8-byte accesses
+  const bool planes = in->theta_sb == 1 && in->target_sb == 1 && in->batch % 2 == 0 && aligned8(in->theta) && in->theta_sj % 2 == 0 &&
+                      aligned8(in->target) && in->target_sc % 2 == 0 &&
+                      (!dyn || (in->obst_sb == 1 && aligned8(in->obstacles) && in->obst_so % 2 == 0 && in->obst_sc % 2 == 0)) &&
+                      (!grad || (dt_sb == 1 && dt_sj % 2 == 0 && aligned8(dtheta)));
   if (planes) return kPlanes;
   return kStrided;
 }
@@ -133,6 +150,7 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   LagrangianParams p;
   memset(&p, 0, sizeof(p));
   fill_uniforms(spec, w->host, p.u);
+  fill_packed_uniforms(spec, p.u, p.pu);
   p.batch = in->batch;
   p.theta = in->theta;    p.th_sb = in->theta_sb;  p.th_sj = in->theta_sj;
   p.target = in->target;  p.tg_sb = in->target_sb; p.tg_sc = in->target_sc;

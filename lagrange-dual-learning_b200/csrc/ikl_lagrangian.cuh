@@ -10,12 +10,15 @@
 // Memory layouts (see IklBatch in include/ikl.h):
 //   kStrided  any element strides, scalar loads, runtime link lengths        -- always-correct fallback
 //   kRows     the reference's own row-major tensors: theta (B,J), target (B,>=2), obstacles (B,4,4)
-//             read as one float4 per obstacle row; one sample per thread, U samples in flight
-//   kPlanes   structure-of-arrays planes: kVec consecutive samples per thread, 16-byte loads/stores
+//             read as one float4 per obstacle row; each thread evaluates the PAIR of samples (b, b + 256) with
+//             packed f32x2 maths (ikl_packed.cuh); the ragged tail runs the scalar per-sample code
+//   kPlanes   structure-of-arrays planes: each thread loads two consecutive samples of every plane with one
+//             8-byte access -- the loaded register pair IS the packed operand -- and stores d/dtheta the same way
 #pragma once
 
 #include "ikl_common.h"
 #include "ikl_device.cuh"
+#include "ikl_packed.cuh"
 
 namespace ikl {
 
@@ -25,10 +28,10 @@ constexpr int kFlushSamples = 64;   // samples a thread adds in fp32 before flus
 constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce
 
 #ifndef IKL_PLANES_VEC
-#define IKL_PLANES_VEC 4
+#define IKL_PLANES_VEC 2          // samples per thread per iteration in the planes layout (the packed pair)
 #endif
 #ifndef IKL_ROWS_UNROLL
-#define IKL_ROWS_UNROLL 2
+#define IKL_ROWS_UNROLL 2         // samples in flight per thread in the strided fallback
 #endif
 #ifndef IKL_MIN_BLOCKS
 #define IKL_MIN_BLOCKS 2
@@ -39,6 +42,7 @@ enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
 
 struct LagrangianParams {
   Uniforms u;
+  PackedUniforms pu;
   long long batch;
   const float* theta;   long long th_sb, th_sj;
   const float* target;  long long tg_sb, tg_sc;
@@ -93,6 +97,13 @@ struct SharedAcc {
     for (int i = 0; i < K; ++i) {
       v[i][threadIdx.x] += (double)acc[i];
       acc[i] = 0.f;
+    }
+  }
+  __device__ __forceinline__ void flush(f2 (&acc)[K]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      v[i][threadIdx.x] += (double)(f2_lo(acc[i]) + f2_hi(acc[i]));
+      acc[i] = f2_splat(0.f);
     }
   }
 };
@@ -255,95 +266,75 @@ __device__ __forceinline__ void run_scalar_layout(const LagrangianParams& p, con
   sacc.flush(acc);
 }
 
-// ---- planes layout: kVec consecutive samples per thread, 16-byte (or 8-byte) accesses ------------------------
-template <int V> struct VecIO;
-template <> struct VecIO<4> {
-  using T = float4;
-  static __device__ __forceinline__ T load(const float* p) { return ldg_stream4(p); }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
-    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-  }
-  static __device__ __forceinline__ float get(const T& t, int i) { return i == 0 ? t.x : i == 1 ? t.y : i == 2 ? t.z : t.w; }
-};
-template <> struct VecIO<2> {
-  using T = float2;
-  static __device__ __forceinline__ T load(const float* p) { return ldg_stream2(p); }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
-    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
-  }
-  static __device__ __forceinline__ float get(const T& t, int i) { return i == 0 ? t.x : t.y; }
-};
+// ---- packed layouts: two samples per thread on the f32x2 pipe ----------------------------------------------------
+__device__ __forceinline__ f2 ldg_stream_f2(const float* p) {
+  f2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f2(float* p, f2 v) {
+  asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-template <class C, class W>
-__device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w, SharedAcc<C::K>& sacc) {
-  constexpr int V = IKL_PLANES_VEC;
-  using IO = VecIO<V>;
-  const long long nvec = p.batch / V;             // the API guarantees batch % V == 0 for this layout
+template <class C>
+__device__ __forceinline__ void static_obstacles_packed(const LagrangianParams& p, f2 (&ob)[C::NOB][3]) {
+#pragma unroll
+  for (int k = 0; k < C::NOB; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ob[k][c] = as_f2(p.pu.stat_ob[k][c]);
+  }
+}
+
+// side outputs of a forward-only launch for the pair (bA, bB): row-major (B,3) / (B,2), rarely requested
+__device__ __forceinline__ void store_side_outputs(const LagrangianParams& p, long long bA, long long bB, const f2 (&ee)[3], f2 tx, f2 ty) {
+  if (p.q_ee) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p.q_ee[bA * 3 + c] = f2_lo(ee[c]);
+      p.q_ee[bB * 3 + c] = f2_hi(ee[c]);
+    }
+  }
+  if (p.err_sq) {
+    const f2 ex = f2_sub(tx, ee[0]), ey = f2_sub(ty, ee[1]);
+    const f2 qx = f2_mul(f2_splat(0.5f), f2_mul(ex, ex)), qy = f2_mul(f2_splat(0.5f), f2_mul(ey, ey));
+    p.err_sq[bA * 2] = f2_lo(qx);  p.err_sq[bA * 2 + 1] = f2_lo(qy);
+    p.err_sq[bB * 2] = f2_hi(qx);  p.err_sq[bB * 2 + 1] = f2_hi(qy);
+  }
+}
+
+// planes: thread v owns samples (2v, 2v+1); every plane access is one coalesced 8-byte load/store.
+template <class C, class W2>
+__device__ __forceinline__ void run_planes_packed(const LagrangianParams& p, const W2& w2, SharedAcc<C::K>& sacc) {
+  const long long npair = p.batch >> 1;             // the API guarantees an even batch for this layout
   const long long step = (long long)gridDim.x * kThreads;
-  float acc[C::K];
+  f2 acc[C::K];
 #pragma unroll
-  for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
   int since_flush = 0;
-  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += step) {
-    const long long b = v * V;
-    typename IO::T th4[C::J], tg4[2], ob4[C::NOB][3];
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < npair; v += step) {
+    const long long b = v << 1;
+    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
 #pragma unroll
-    for (int j = 0; j < C::J; ++j) th4[j] = IO::load(p.theta + j * p.th_sj + b);
-    tg4[0] = IO::load(p.target + b);
-    tg4[1] = IO::load(p.target + p.tg_sc + b);
+    for (int j = 0; j < 3; ++j) th[j] = ldg_stream_f2(p.theta + j * p.th_sj + b);
+    const f2 tx = ldg_stream_f2(p.target + b);
+    const f2 ty = ldg_stream_f2(p.target + p.tg_sc + b);
     if (C::DYN) {
 #pragma unroll
       for (int k = 0; k < C::NOBS; ++k) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ob4[k][c] = IO::load(p.obst + k * p.ob_so + c * p.ob_sc + b);
+        for (int c = 0; c < 3; ++c) ob[k][c] = ldg_stream_f2(p.obst + k * p.ob_so + c * p.ob_sc + b);
       }
+    } else {
+      static_obstacles_packed<C>(p, ob);
     }
-    float out[C::J][V], eeo[3][V];
-#pragma unroll
-    for (int sidx = 0; sidx < V; ++sidx) {
-      float th[C::J], ob[C::NOB][3], dth[C::J], ee[3];
-#pragma unroll
-      for (int j = 0; j < C::J; ++j) th[j] = IO::get(th4[j], sidx);
-      if (C::DYN) {
-#pragma unroll
-        for (int k = 0; k < C::NOBS; ++k) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) ob[k][c] = IO::get(ob4[k][c], sidx);
-        }
-      } else {
-        static_obstacles<C>(p, ob);
-      }
-      const float tx = IO::get(tg4[0], sidx), ty = IO::get(tg4[1], sidx);
-      eval_sample<C::J, C::NOBS, C::JL, C::GRAD, C::UNIT>(p.u, w, th, tx, ty, ob, acc, dth, ee);
-      if (C::GRAD) {
-#pragma unroll
-        for (int j = 0; j < C::J; ++j) out[j][sidx] = dth[j];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) eeo[c][sidx] = ee[c];
-      }
-    }
+    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
     if (C::GRAD) {
 #pragma unroll
-      for (int j = 0; j < C::J; ++j) IO::store(p.dtheta + j * p.dt_sj + b, out[j]);
+      for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
     } else {
-      if (p.q_ee) {                               // row-major (B,3) / (B,2) side outputs, rarely requested
-#pragma unroll
-        for (int sidx = 0; sidx < V; ++sidx) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) p.q_ee[(b + sidx) * 3 + c] = eeo[c][sidx];
-        }
-      }
-      if (p.err_sq) {
-#pragma unroll
-        for (int sidx = 0; sidx < V; ++sidx) {
-          const float ex = IO::get(tg4[0], sidx) - eeo[0][sidx], ey = IO::get(tg4[1], sidx) - eeo[1][sidx];
-          p.err_sq[(b + sidx) * 2] = 0.5f * (ex * ex);
-          p.err_sq[(b + sidx) * 2 + 1] = 0.5f * (ey * ey);
-        }
-      }
+      store_side_outputs(p, b, b + 1, ee, tx, ty);
     }
-    if (++since_flush == kFlushSamples / V) {
+    if (++since_flush == kFlushSamples / 2) {
       since_flush = 0;
       sacc.flush(acc);
     }
@@ -351,16 +342,108 @@ __device__ __forceinline__ void run_planes(const LagrangianParams& p, const W& w
   sacc.flush(acc);
 }
 
+// rows: thread t of a 512-sample tile owns samples (base + t, base + t + 256); the ragged tail (< 512 samples)
+// goes through the scalar per-sample code so any batch size is accepted.
+template <class C, class W2, class W>
+__device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const W2& w2, const W& w, SharedAcc<C::K>& sacc) {
+  constexpr int kTile = 2 * kThreads;
+  const long long B = p.batch;
+  const long long full = (B / kTile) * kTile;
+  f2 acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  int since_flush = 0;
+  for (long long base = (long long)blockIdx.x * kTile; base < full; base += (long long)gridDim.x * kTile) {
+    const long long bA = base + threadIdx.x, bB = bA + kThreads;
+    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    const float* tA = p.theta + bA * 3;
+    const float* tB = p.theta + bB * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) th[j] = f2_make(ldg_stream1(tA + j), ldg_stream1(tB + j));
+    const float* gA = p.target + bA * p.tg_sb;
+    const float* gB = p.target + bB * p.tg_sb;
+    const f2 tx = f2_make(ldg_stream1(gA), ldg_stream1(gB));
+    const f2 ty = f2_make(ldg_stream1(gA + 1), ldg_stream1(gB + 1));
+    if (C::DYN) {
+      const float* oA = p.obst + bA * (4 * kMaxObst);
+      const float* oB = p.obst + bB * (4 * kMaxObst);
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+        const float4 a = ldg_stream4(oA + 4 * k), b4 = ldg_stream4(oB + 4 * k);
+        ob[k][0] = f2_make(a.x, b4.x);
+        ob[k][1] = f2_make(a.y, b4.y);
+        ob[k][2] = f2_make(a.z, b4.z);
+      }
+    } else {
+      static_obstacles_packed<C>(p, ob);
+    }
+    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    if (C::GRAD) {
+      float* dA = p.dtheta + bA * 3;
+      float* dB = p.dtheta + bB * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dA[j] = f2_lo(dth[j]);
+        dB[j] = f2_hi(dth[j]);
+      }
+    } else {
+      store_side_outputs(p, bA, bB, ee, tx, ty);
+    }
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      sacc.flush(acc);
+    }
+  }
+  sacc.flush(acc);
+  // ragged tail, one sample per thread
+  float sacc1[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) sacc1[i] = 0.f;
+  for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < B; b += (long long)gridDim.x * kThreads) {
+    float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3];
+    if (!C::DYN) static_obstacles<C>(p, ob);
+    load_sample<C>(p, b, th, tx, ty, ob);
+    eval_sample<3, C::NOBS, C::JL, C::GRAD, true>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
+    store_sample<C>(p, b, dth, ee, tx, ty);
+  }
+  sacc.flush(sacc1);
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
   __shared__ SharedAcc<C::K> sacc;
+  __shared__ float2 s_lam2[kMaxK];
   sacc.clear();
-  if (C::MODE == kGradDevW) {
-    const DeviceWeights<C::K> w(p.u, p.w_dev);
-    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, sacc); else run_scalar_layout<C>(p, w, sacc);
+  if constexpr (C::LAYOUT == kStrided) {
+    if constexpr (C::MODE == kGradDevW) {
+      const DeviceWeights<C::K> w(p.u, p.w_dev);
+      run_scalar_layout<C>(p, w, sacc);
+    } else {
+      const HostWeights w(p.u, nullptr);
+      run_scalar_layout<C>(p, w, sacc);
+    }
+  } else if constexpr (C::MODE == kGradDevW) {
+    // device-resident multipliers: stage the duplicated pairs once per block
+    if (threadIdx.x < C::K) {
+      const float l = __ldg(p.w_dev + threadIdx.x);
+      s_lam2[threadIdx.x] = make_float2(l, l);
+    }
+    __syncthreads();
+    const PackedSmemWeights w2{s_lam2};
+    if constexpr (C::LAYOUT == kPlanes) {
+      run_planes_packed<C>(p, w2, sacc);
+    } else {
+      const DeviceWeights<C::K> w(p.u, p.w_dev);
+      run_rows_packed<C>(p, w2, w, sacc);
+    }
   } else {
-    const HostWeights w(p.u, nullptr);
-    if (C::LAYOUT == kPlanes) run_planes<C>(p, w, sacc); else run_scalar_layout<C>(p, w, sacc);
+    const PackedHostWeights w2{p.pu};
+    if constexpr (C::LAYOUT == kPlanes) {
+      run_planes_packed<C>(p, w2, sacc);
+    } else {
+      const HostWeights w(p.u, nullptr);
+      run_rows_packed<C>(p, w2, w, sacc);
+    }
   }
   finalize_sums<C::K>(p, sacc);
 }
@@ -375,7 +458,7 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
     if (e != cudaSuccess) return e;
     blocks_per_sm = n > 0 ? n : 1;
   }
-  const long long per_block = (long long)kThreads * (C::LAYOUT == kPlanes ? IKL_PLANES_VEC : IKL_ROWS_UNROLL);
+  const long long per_block = (long long)kThreads * (C::LAYOUT == kStrided ? IKL_ROWS_UNROLL : 2);
   long long tiles = (p.batch + per_block - 1) / per_block;
   if (tiles < 1) tiles = 1;
   long long grid = (long long)sm_count() * blocks_per_sm;

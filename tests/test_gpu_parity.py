@@ -38,13 +38,22 @@ def specs_for(name, good=0.005, bad=1.0):
 
 
 def oracle_truth(ospec, theta, q_des, obst, lam):
-  """fp64 oracle: sums, per-sample terms, closed-form gradient and the near-kink mask."""
+  """fp64 oracle: sums, per-sample terms, closed-form gradient and the mask of samples whose gradient is not a
+  fair fp32 comparison: near a kink of a piecewise-linear penalty, or with a tip within 2e-2 of an obstacle centre
+  (the direction (p - c)/d amplifies the ~1e-7 fp32 round-off of the tip position by 1/d, for ANY fp32 evaluation,
+  the reference's included)."""
   th, qd, ob = theta.double(), q_des.double(), obst.double()
   out = O.lagrangian(th, qd, torch.as_tensor(lam).double(), ospec, ob if ospec.dynamic else None, per_sample=True)
   terms = out["per_sample_terms"].numpy()
   _, dth = O.lagrangian_grad_closed_form(th.numpy(), qd.numpy(), np.asarray(lam, dtype=np.float64), ospec,
                                          ob.numpy() if ospec.dynamic else None)
   kink = (np.abs(terms[:, 1:]) < 1e-6).any(axis=1) if terms.shape[1] > 1 else np.zeros(len(terms), bool)
+  if ospec.enforce_obstacles and len(terms):
+    table = O.obstacle_table(ospec, len(terms), ob if ospec.dynamic else None, torch.float64).double()
+    for tip in O.forward_kinematics(th, ospec.link_lengths):
+      for o in range(ospec.num_obstacles):
+        d = torch.sqrt((tip[:, 0] - table[:, o, 0]) ** 2 + (tip[:, 1] - table[:, o, 1]) ** 2)
+        kink |= (d < 2e-2).numpy()
   return out["constraint_violations"].numpy(), np.abs(terms).sum(axis=0), dth, kink, out
 
 
@@ -262,7 +271,7 @@ def test_fused_vs_oracle_seeded_batches(B, layout, cuda_device, monkeypatch):
     assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums), name
     assert np.all(np.abs(viol - ref32["constraint_violations"].numpy()) <= RTOL * abs_sums), name
     close(loss, float((lam * sums64).sum()), scale=float((lam * abs_sums).sum()))
-    assert kink.mean() < 1e-3
+    assert kink.mean() < 3e-3
     close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
     close(dth[~kink], ref32["dtheta"].numpy()[~kink], scale=np.abs(dth64).max())
 
@@ -277,7 +286,7 @@ def test_fused_vs_oracle_one_million(cuda_device, monkeypatch):
   for layout in ("rows", "planes"):
     viol, loss, dth, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
     assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums)
-    assert kink.mean() < 1e-3
+    assert kink.mean() < 3e-3
     close(dth[~kink], dth64[~kink], scale=np.abs(dth64).max())
 
 
@@ -334,7 +343,7 @@ def test_autograd_function_and_general_upstream_gradients(cuda_device):
   th_ref = theta.double().requires_grad_(True)
   out = O.lagrangian(th_ref, q_des.double(), lam.double(), ospec, obst.double(), per_sample=True)
   (2.5 * out["lagrange_loss"] + (gv.double() * out["constraint_violations"]).sum()).backward()
-  kink = (out["per_sample_terms"].detach().numpy()[:, 1:].__abs__() < 1e-6).any(axis=1)
+  kink = oracle_truth(ospec, theta, q_des, obst, lam.numpy())[3]
   dev = cuda_device
   th = theta.to(dev).requires_grad_(True)
   viol, loss = fused.ik_lagrangian(th, q_des.to(dev), obst.to(dev), lam.to(dev), spec)
