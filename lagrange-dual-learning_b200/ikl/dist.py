@@ -1,0 +1,94 @@
+"""Multi-GPU plumbing of the dual-learning step (one process per GPU, torch.distributed; NCCL over NVLink on a B200
+box, gloo in the CPU tests).
+
+The reference has no distributed code; the path shards trivially because every constraint value is a SUM over samples
+(scripts/trainer.py:195,204,239) and the loss gradient is therefore a sum of per-shard gradients:
+
+  train step   every rank runs the fused kernel on its shard of the batch, back-propagates through its replica of the
+               network, then ONE all-reduce(sum) of a flat fp32 buffer [all parameter gradients | K violation sums]
+               makes gradients and logged sums global; identical Adam steps keep the replicas in lock-step.
+  dual step    ranks accumulate the K sums over their validation shard (float64 on device), one all-reduce(sum) of K
+               doubles, then the same lambda <- max(0, lambda + lr * sum) everywhere.  NCCL returns bit-identical
+               results on all ranks, so lambda cannot drift.
+
+No rescaling by world size anywhere: sums, not means.
+"""
+import torch
+import torch.distributed as dist
+from torch.utils.data import DataLoader
+from torch.utils.data.distributed import DistributedSampler
+
+
+def is_distributed():
+  return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rank():
+  return dist.get_rank() if is_distributed() else 0
+
+
+def world_size():
+  return dist.get_world_size() if is_distributed() else 1
+
+
+def broadcast_parameters(model, src=0):
+  """Start every replica from rank 0's initial weights."""
+  if not is_distributed():
+    return
+  with torch.no_grad():
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    dist.broadcast(flat, src)
+    offset = 0
+    for p in model.parameters():
+      n = p.numel()
+      p.copy_(flat[offset:offset + n].view_as(p))
+      offset += n
+
+
+def all_reduce_gradients(model, extra=None):
+  """Sum parameter gradients (and, if given, the 1-D fp32 tensor `extra`, e.g. the K violation sums) over ranks in
+  one flat collective.  `extra` is updated in place.  No-op on a single process."""
+  if not is_distributed():
+    return
+  grads = [p.grad for p in model.parameters() if p.grad is not None]
+  pieces = [g.reshape(-1) for g in grads]
+  if extra is not None:
+    pieces.append(extra.detach().reshape(-1).to(pieces[0].dtype if pieces else extra.dtype))
+  if not pieces:
+    return
+  flat = torch.cat(pieces)
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+  offset = 0
+  for g in grads:
+    n = g.numel()
+    g.copy_(flat[offset:offset + n].view_as(g))
+    offset += n
+  if extra is not None:
+    with torch.no_grad():
+      extra.copy_(flat[offset:offset + extra.numel()].view_as(extra))
+
+
+def all_reduce_sum(t):
+  """In-place sum over ranks (the K running violation sums of the dual step)."""
+  if is_distributed():
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  return t
+
+
+def shard_bounds(n, r=None, w=None):
+  """[start, end) of rank r's contiguous shard of n items (ragged tails go to the low ranks)."""
+  r = rank() if r is None else r
+  w = world_size() if w is None else w
+  base, rem = divmod(n, w)
+  start = r * base + min(r, rem)
+  return start, start + base + (1 if r < rem else 0)
+
+
+def make_loader(dataset, batch_size, num_workers):
+  """The reference's DataLoader(dataset, batch_size, shuffle=True) (trainer.py:155-156); under torch.distributed each rank
+  draws its share of every global batch through a DistributedSampler (batch_size is the GLOBAL batch size)."""
+  if not is_distributed():
+    return DataLoader(dataset, batch_size, True, num_workers=num_workers)
+  per_rank = max(1, batch_size // world_size())
+  sampler = DistributedSampler(dataset, num_replicas=world_size(), rank=rank(), shuffle=True, drop_last=False)
+  return DataLoader(dataset, per_rank, sampler=sampler, num_workers=num_workers)

@@ -1,0 +1,164 @@
+"""GPU tests of the callers either side of the hot path: dataset generation, the trainer mirror (fused vs op-by-op
+process_batch), and lambda / weight trajectories against a run of the UNMODIFIED reference trainer
+(tests/golden/dual_trajectory_*.pt, produced by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, config_json
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_1obs_static")
+
+
+def make_trainer(name, tmp_path, fx, extra=()):
+  from ikl.configs import write_config
+  from kinematics.dataset import IkDataset
+  from models.simple_network import SimpleNetwork
+  from scripts.options import Options
+  from scripts.trainer import IkLagrangeDualTrainer
+  cfg = config_json(name)
+  cfg_path = write_config(cfg, str(tmp_path / (name + ".json")))
+  o = fx["opt"]
+  argv = ["--model_name", "t", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--num_workers", "0"]
+  for k in ("batch_size", "lagrange_iters", "train_iters", "optimizer_lr", "multiplier_lr", "hidden_units", "initial_lambda",
+            "penalty_good_slope", "penalty_bad_slope", "train_dataset_size", "val_dataset_size", "model_save_hz"):
+    argv += ["--" + k, str(o[k])]
+  opt = Options().parse(argv + list(extra))
+  datasets = (IkDataset.from_tensors(cfg, fx["train"]), IkDataset.from_tensors(cfg, fx["val"]))
+  tr = IkLagrangeDualTrainer(opt, datasets=datasets)
+  # the fixture run removed dropout (p = 0) so that it does not depend on the device's RNG
+  tr.model = SimpleNetwork(20, 3, hidden_units=opt.hidden_units, depth=8, dropout=0.0).to(tr.device)
+  tr.model.load_state_dict(fx["init_state"])
+  tr.optimizer = torch.optim.Adam(tr.model.parameters(), lr=opt.optimizer_lr, betas=(0.9, 0.999))
+  return tr
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_dataset_generation_reproduces_the_reference(name, cuda_device):
+  from kinematics.dataset import IkDataset
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  for split, n in (("train", 64), ("val", 32)):
+    ds = IkDataset(n, 3, config_json(name))          # seed 0, like the reference trainer (trainer.py:150-153)
+    ref = fx[split]
+    assert len(ds) == n
+    assert torch.equal(ds.tensor_template, ref["tensor_template"])
+    assert torch.equal(ds.random_theta, ref["random_theta"]), "same random stream, same accept/reject decisions"
+    torch.testing.assert_close(ds.random_ee, ref["random_ee"], rtol=1e-5, atol=3e-6)
+    if ref["random_obstacles"] is None:
+      assert ds.random_obstacles is None
+    else:
+      assert torch.equal(ds.random_obstacles, ref["random_obstacles"])
+    item = ds[3]
+    assert item["input_tensor"].shape == (20,) and item["q_ee_desired"].shape == (3,) and item["joint_theta"].shape == (3,)
+    assert torch.equal(item["input_tensor"][:2], ds.random_ee[3, :2])
+    if ds.random_obstacles is not None:
+      assert item["dynamic_obstacles"].shape == (4, 4) and torch.equal(item["input_tensor"][4:], ds.random_obstacles[3].flatten())
+
+
+def test_dataset_leaves_the_global_generator_where_the_reference_would(cuda_device):
+  """Block-wise drawing must not consume more of torch's CPU stream than draw-by-draw rejection sampling."""
+  from kinematics.dataset import IkDataset
+  cfg = config_json("cfg_joint_limits_and_4obs_dynamic")
+  ds = IkDataset(16, 3, cfg, seed=5)
+  after = torch.rand(4)
+  # replay by hand: N*J angles, then one 2-vector per accepted or rejected candidate
+  torch.manual_seed(5)
+  torch.empty(16, 3).uniform_(-2.094395, 2.094395)
+  n_candidates = 0
+  from kinematics.penalties import no_joint_collisions_circle
+  from kinematics.forward_kinematics import ForwardKinematicsThreeLinkTorch
+  tips = ForwardKinematicsThreeLinkTorch(ds.random_theta)
+  for i in range(16):
+    q = [t[i] for t in tips]
+    for o in range(4):
+      xy = torch.empty(2).uniform_(-1.2, 1.2)
+      while not no_joint_collisions_circle(q, xy[0], xy[1], cfg["dynamic_constraints"]["random_obstacles_template"]):
+        xy = torch.empty(2).uniform_(-1.2, 1.2)
+      assert torch.equal(xy, ds.random_obstacles[i, o, :2])
+  assert torch.equal(torch.rand(4), after)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fused_and_unfused_process_batch_agree(name, tmp_path, cuda_device):
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  tr = make_trainer(name, tmp_path, fx)
+  inputs = next(iter(tr.train_loader))
+  lam = torch.linspace(0.5, 2.0, len(tr.lambda_multipliers), device=tr.device)
+  fused_out = tr.process_batch({k: v.clone() for k, v in inputs.items()}, lam)
+  tr.model.zero_grad()
+  fused_out["lagrange_loss"].backward()
+  g_fused = [p.grad.clone() for p in tr.model.parameters()]
+  plain = tr.process_batch_unfused({k: v.clone() for k, v in inputs.items()}, lam)
+  tr.model.zero_grad()
+  plain["lagrange_loss"].backward()
+  assert set(plain.keys()) <= set(fused_out.keys())
+  for key in ("pred_joint_theta", "q_ee_actual", "joint_angle_l2", "position_err_sq", "constraint_violations", "lagrange_loss"):
+    a, b = fused_out[key].detach().cpu(), plain[key].detach().cpu()
+    assert a.shape == b.shape, key
+    scale = float(b.abs().max()) if key != "constraint_violations" else float(b.abs().sum())
+    assert float((a - b).abs().max()) <= 1e-5 * max(scale, 1e-6), key
+  for a, p in zip(g_fused, tr.model.parameters()):
+    assert float((a - p.grad).abs().max()) <= 2e-5 * max(float(p.grad.abs().max()), 1e-6)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_lambda_and_weight_trajectory_match_the_reference_trainer(name, tmp_path, cuda_device):
+  """6 dual epochs (Adam step + dual-ascent step each) from the same initial weights and datasets as a run of the
+  reference's own IkLagrangeDualTrainer on the CPU: lambda after every epoch within 1e-5 (relative to max lambda)."""
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  tr = make_trainer(name, tmp_path, fx)
+  hist = fx["lambda_history"]
+  torch.testing.assert_close(tr.lambda_multipliers.cpu(), hist[0])
+  for epoch in range(hist.shape[0] - 1):
+    tr.train_with_relaxation(tr.lambda_multipliers)
+    tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
+    got, want = tr.lambda_multipliers.cpu().double(), hist[epoch + 1].double()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), (epoch, got, want)
+  for k, v in tr.model.state_dict().items():
+    assert float((v.cpu() - fx["final_state"][k]).abs().max()) <= 2e-5 * max(1.0, float(fx["final_state"][k].abs().max())), k
+  # the isolated dual step over 4 validation batches of 8 (sum over batches, trainer.py:274-280)
+  tr.model.load_state_dict(fx["final_state"])
+  tr.val_loader = torch.utils.data.DataLoader(tr.val_dataset, 8, False, num_workers=0)
+  lam_iso = tr.update_multipliers(hist[0].to(tr.device))
+  assert float((lam_iso.cpu() - fx["lambda_isolated_step"]).abs().max()) <= 1e-5 * float(fx["lambda_isolated_step"].abs().max())
+
+
+def test_trainer_main_runs_and_writes_the_reference_artifacts(tmp_path, cuda_device):
+  """A miniature end-to-end run through main(): log files, checkpoints in the reference's layout, validate()."""
+  from ikl.configs import write_config
+  from scripts.options import Options
+  from scripts.trainer import IkLagrangeDualTrainer
+  name = "cfg_joint_limits_and_4obs_dynamic"
+  cfg_path = write_config(config_json(name), str(tmp_path / "cfg.json"))
+  opt = Options().parse(["--model_name", "mini", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--num_workers", "0",
+                         "--train_dataset_size", "64", "--val_dataset_size", "32", "--batch_size", "8", "--lagrange_iters", "3",
+                         "--train_iters", "4", "--model_save_hz", "1", "--hidden_units", "16", "--initial_lambda", "1",
+                         "--penalty_good_slope", "0.005", "--cache_save_path", str(tmp_path)])
+  tr = IkLagrangeDualTrainer(opt)
+  lam0 = tr.lambda_multipliers.clone()
+  tr.main()
+  log = tmp_path / "mini"
+  assert (log / "opt.json").exists() and (log / "config.json").exists()
+  names = (log / "constraint_names.txt").read_text().strip().splitlines()
+  assert names[0] == "0,EE" and names[-1] == "15,DYN_OB4_J3" and len(names) == 16
+  for e in (1, 2):
+    for f in ("model.pth", "adam.pth", "multipliers.pth"):
+      assert (log / "models" / ("weights_%d" % e) / f).exists()
+  assert (tmp_path / "mini_train.pt").exists() and (tmp_path / "mini_val.pt").exists()      # dataset cache files
+  assert tr.lambda_multipliers.shape == lam0.shape and bool((tr.lambda_multipliers >= 0).all())
+  assert not torch.equal(tr.lambda_multipliers, lam0)
+  saved = torch.load(log / "models" / "weights_2" / "multipliers.pth", map_location="cpu")
+  assert torch.equal(saved, tr.lambda_multipliers.cpu())
+  # a second trainer picks the cached datasets up and can resume weights + multipliers
+  opt2 = Options().parse(["--model_name", "mini", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--num_workers", "0",
+                          "--train_dataset_size", "64", "--val_dataset_size", "32", "--hidden_units", "16",
+                          "--cache_save_path", str(tmp_path), "--load_weights_folder", str(log / "models" / "weights_2"),
+                          "--load_adam", "--load_multipliers"])
+  tr2 = IkLagrangeDualTrainer(opt2)
+  assert torch.equal(tr2.lambda_multipliers.cpu(), saved)
+  for a, b in zip(tr.model.parameters(), tr2.model.parameters()):
+    assert torch.equal(a, b)

@@ -1,0 +1,176 @@
+"""CPU tests of the host-side mirror: options, checkpoint helpers, network, constraint layout, multi-process plumbing
+(gloo, world_size 2).  Nothing here launches a kernel."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, PKG, ROOT, config_json
+from oracle import ik_oracle as O
+
+REF = "/root/reference"
+
+
+def test_options_have_the_reference_flags_and_defaults():
+  from scripts.options import Options
+  opt = Options().parse(["--model_name", "m", "--config_file", "c.json"])
+  want = dict(lagrange_iters=1000, train_iters=500, batch_size=8, train_dataset_size=32000, val_dataset_size=4000,
+              multiplier_lr=1e-4, optimizer_lr=1e-4, initial_lambda=40, num_links=3, num_workers=4, model_save_hz=200,
+              hidden_units=40, penalty_bad_slope=1.0, penalty_good_slope=0.1, load_adam=False, load_weights_folder=None,
+              cache_save_path=None, show_groundtruth_theta=False, no_plot=False)
+  for k, v in want.items():
+    assert getattr(opt, k) == v, k
+  with pytest.raises(SystemExit):
+    Options().parse(["--num_links", "5"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted (GPU box)")
+def test_options_match_reference_parser_when_mounted():
+  import importlib.util
+  from scripts.options import Options
+  spec = importlib.util.spec_from_file_location("ref_options", os.path.join(REF, "scripts", "options.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)         # its `from utils.paths import top_folder` resolves to our utils.paths
+  ref_actions = {a.dest: a for a in mod.Options().parser._actions if a.dest != "help"}
+  our_actions = {a.dest: a for a in Options().parser._actions if a.dest != "help"}
+  for dest, a in ref_actions.items():
+    assert dest in our_actions, dest
+    if dest != "log_dir":
+      assert our_actions[dest].default == a.default, dest
+    assert our_actions[dest].type == a.type, dest
+
+
+def test_simple_network_matches_reference_architecture():
+  from models.simple_network import SimpleNetwork
+  from utils.training_utils import count_parameters
+  net = SimpleNetwork(20, 3, hidden_units=100, depth=8, dropout=0.05)
+  assert count_parameters(net) == 83203
+  keys = list(net.state_dict().keys())
+  assert keys[:2] == ["input.weight", "input.bias"] and "hidden.7.0.weight" in keys and keys[-1] == "output.bias"
+  assert net(torch.zeros(5, 20)).shape == (5, 3)
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_cfg_joint_limits_and_4obs_dynamic.pt"))
+  small = SimpleNetwork(20, 3, hidden_units=16, depth=8, dropout=0.0)
+  small.load_state_dict(fx["init_state"])                   # state_dict written by the reference's own SimpleNetwork
+
+
+def test_checkpoint_helpers_roundtrip(tmp_path):
+  from models.simple_network import SimpleNetwork
+  from utils import training_utils as tu
+  net = SimpleNetwork(20, 3, hidden_units=8, depth=2)
+  adam = torch.optim.Adam(net.parameters(), lr=1e-3)
+  net(torch.randn(4, 20)).sum().backward()
+  adam.step()
+  mp_, ap_ = tu.save_model(net, adam, str(tmp_path), 7)
+  assert mp_.endswith(os.path.join("weights_7", "model.pth")) and ap_.endswith(os.path.join("weights_7", "adam.pth"))
+  lam = torch.tensor([1.0, 0.0, 2.5])
+  lp = tu.save_multipliers(lam, str(tmp_path), 7)
+  assert lp.endswith(os.path.join("weights_7", "multipliers.pth"))
+  torch.testing.assert_close(torch.load(lp), lam)            # raw tensor, the reference's format
+  torch.testing.assert_close(tu.load_multipliers(str(tmp_path), 7), lam)
+  net2 = SimpleNetwork(20, 3, hidden_units=8, depth=2)
+  adam2 = torch.optim.Adam(net2.parameters(), lr=1e-3)
+  tu.load_model(net2, adam2, mp_, ap_)
+  for a, b in zip(net.parameters(), net2.parameters()):
+    assert torch.equal(a, b)
+  assert tu.save_model(net, None, str(tmp_path), 8)[1] is None
+  assert tu.get_best_system_device() in ("cuda", "mps", "cpu")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted (GPU box)")
+def test_shipped_multipliers_load_and_fit_the_constraint_layout():
+  from ikl import ConstraintSpec
+  from utils.training_utils import load_multipliers
+  table = {"cfg_no_constraints": "ik_threelink_position/models/weights_600", "cfg_joint_limits": "ik_threelink_joint_limits/models/weights_200",
+           "cfg_joint_limits_and_1obs_static": "ik_threelink_obs1/models/weights_950",
+           "cfg_joint_limits_and_4obs_static": "ik_threelink_obs4/models/weights_950",
+           "cfg_joint_limits_and_4obs_dynamic": "ik_threelink_obs4_dyn/models/weights_650"}
+  for name, folder in table.items():
+    lam = load_multipliers(os.path.join(REF, "resources/pretrained_models", folder))      # saved on a CUDA device
+    spec = ConstraintSpec.from_config(config_json(name), 3)
+    assert lam.dtype == torch.float32 and lam.numel() == spec.num_constraints == len(spec.constraint_names)
+
+
+# ---- multi-process (gloo, world_size 2) ---------------------------------------------------------------------------
+def _worker(rank, world, port, tmpdir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  for p in (ROOT, PKG):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from ikl import dist as D, synthetic
+    from ikl.configs import standard_config
+    from models.simple_network import SimpleNetwork
+    assert D.is_distributed() and D.rank() == rank and D.world_size() == world
+    # replicas start identical
+    torch.manual_seed(100 + rank)
+    net = SimpleNetwork(20, 3, hidden_units=8, depth=2, dropout=0.0)
+    D.broadcast_parameters(net)
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+    # the dual-learning exchange: batch sharded contiguously, one flat all-reduce of [grads | K sums]
+    cfg = standard_config("cfg_joint_limits_and_4obs_dynamic")
+    ospec = O.spec_from_json(cfg, 3, 0.005, 1.0)
+    B = 103                                             # ragged on purpose
+    theta_in = torch.randn(B, 20, generator=torch.Generator().manual_seed(5))
+    _, q_des, obst = synthetic.make_batch(B, seed=3)
+    lam = torch.linspace(0.5, 2.0, 16)
+    lo, hi = D.shard_bounds(B)
+    assert (lo, hi) == ((0, 52) if rank == 0 else (52, 103))
+    out = O.lagrangian(net(theta_in[lo:hi]), q_des[lo:hi], lam, ospec, obst[lo:hi])
+    net.zero_grad()
+    out["lagrange_loss"].backward()
+    viol = out["constraint_violations"].detach().clone()
+    D.all_reduce_gradients(net, extra=viol)
+    # single-process truth on the whole batch
+    ref_net = SimpleNetwork(20, 3, hidden_units=8, depth=2, dropout=0.0)
+    ref_net.load_state_dict(net.state_dict())
+    ref = O.lagrangian(ref_net(theta_in), q_des, lam, ospec, obst)
+    ref["lagrange_loss"].backward()
+    for p, q in zip(net.parameters(), ref_net.parameters()):
+      torch.testing.assert_close(p.grad, q.grad, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(viol, ref["constraint_violations"].detach(), rtol=1e-5, atol=1e-5)
+    # dual step: float64 running sums, all-reduce, identical lambda everywhere
+    total = out["constraint_violations"].detach().double()
+    D.all_reduce_sum(total)
+    lam_new = O.dual_update(lam, total.float().unsqueeze(0), 1e-3)
+    both = [torch.zeros_like(lam_new) for _ in range(world)]
+    dist.all_gather(both, lam_new)
+    assert torch.equal(both[0], both[1]), "lambda must be bit-identical on every rank"
+    torch.testing.assert_close(lam_new, O.dual_update(lam, ref["constraint_violations"].detach().unsqueeze(0), 1e-3), rtol=1e-5, atol=1e-6)
+    # loaders: the ranks' shares of an epoch partition the dataset
+    ds = torch.utils.data.TensorDataset(torch.arange(40))
+    loader = D.make_loader(ds, 8, 0)
+    seen = torch.cat([b[0] for b in loader])
+    assert loader.batch_size == 4 and len(seen) == 20
+    allseen = [torch.zeros_like(seen) for _ in range(world)]
+    dist.all_gather(allseen, seen)
+    assert sorted(torch.cat(allseen).tolist()) == list(range(40))
+    with open(os.path.join(tmpdir, "ok_%d" % rank), "w") as f:
+      f.write("ok")
+  finally:
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange(tmp_path):
+  import socket
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert os.path.exists(tmp_path / "ok_0") and os.path.exists(tmp_path / "ok_1")
+
+
+def test_single_process_dist_helpers_are_noops():
+  from ikl import dist as D
+  assert not D.is_distributed() and D.rank() == 0 and D.world_size() == 1
+  assert D.shard_bounds(10) == (0, 10) and D.shard_bounds(10, 1, 3) == (4, 7) and D.shard_bounds(10, 2, 3) == (7, 10)
+  t = torch.ones(3)
+  assert D.all_reduce_sum(t) is t
