@@ -1,11 +1,25 @@
-"""python scripts/train.py --model_name ... --config_file ...   (reference: scripts/train.py:6-9)"""
+"""python scripts/train.py --model_name ... --config_file ...   (reference: scripts/train.py:6-9)
+
+Under torchrun (WORLD_SIZE > 1) every process binds to its LOCAL_RANK GPU and joins an NCCL group before the trainer is
+built; the trainer then shards each batch over the ranks (ikl/dist.py)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.realpath(__file__)), "..")))
 
 from scripts.options import Options  # noqa: E402
-from scripts.trainer import IkLagrangeDualTrainer  # noqa: E402
+
+
+def main(argv=None):
+  opt = Options().parse(argv)
+  if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+  from scripts.trainer import IkLagrangeDualTrainer
+  IkLagrangeDualTrainer(opt).main()
+
 
 if __name__ == "__main__":
-  IkLagrangeDualTrainer(Options().parse()).main()
+  main()
