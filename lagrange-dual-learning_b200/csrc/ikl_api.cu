@@ -172,6 +172,15 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   v.mode = !grad ? kFwd : (w->host ? kGradHostW : kGradDevW);
 
   int layout = detect_layout(spec, in, grad, dtheta, dt_sb, dt_sj);
+  if (layout == kPlanes) {
+    // the bulk-async staged kernel moves whole 16-byte multiples: batch % 4 == 0 and 16-byte aligned planes
+    const bool dyn = v.dyn;
+    const char* e = getenv("IKL_PLANES_TMA");
+    const bool want = !(e && e[0] == '0');
+    p.use_tma = want && in->batch % 4 == 0 && in->batch >= 4 && aligned16(in->theta) && in->theta_sj % 4 == 0 && aligned16(in->target) &&
+                in->target_sc % 4 == 0 &&
+                (!dyn || (aligned16(in->obstacles) && in->obst_so % 4 == 0 && in->obst_sc % 4 == 0));
+  }
   const int forced = forced_layout();
   if (forced == kStrided) layout = kStrided;                 // the generic kernel accepts anything
   else if (forced >= 0 && forced != layout) return IKL_ERR_INVALID_ARGUMENT;   // tests: demand a fast layout or fail loudly

@@ -56,6 +56,7 @@ struct LagrangianParams {
   float* viol_out;
   float* loss_out;
   double* viol_accum;   // or null
+  int use_tma;          // planes layout: bulk-async staged kernel (needs batch % 4 == 0 and 16-byte aligned planes)
 };
 
 template <int LAYOUT_, int J_, int NOBS_, bool DYN_, bool JL_, int MODE_, bool UNIT_>
@@ -409,6 +410,160 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
   sacc.flush(sacc1);
 }
 
+// ---- planes layout, bulk-async staged (TMA 1-D copies + mbarrier) -------------------------------------------------
+// Each 512-sample tile of every plane is a contiguous 2 KiB run in HBM.  One elected thread issues one
+// cp.async.bulk (SASS UBLKCP) per plane into a shared-memory stage and arms the stage's mbarrier with the byte count;
+// the 256 compute threads wait on the barrier, read their pair of samples with LDS.64 at immediate offsets (no
+// per-plane address arithmetic, no long-scoreboard stalls) and write d/dtheta straight to HBM.  Two stages: tile k+1
+// is in flight while tile k is evaluated.
+constexpr int kTmaTile = 2 * kThreads;                 // samples per tile
+constexpr int kTmaStages = 2;
+constexpr int kTmaPlaneBytes = kTmaTile * 4;           // 2048
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "IKL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni IKL_DONE;\n"
+      "bra.uni IKL_WAIT;\n"
+      "IKL_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class C>
+struct TmaLayout {
+  static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
+  static constexpr int kStageBytes = kPlanes * kTmaPlaneBytes;
+  static constexpr size_t kSmemBytes = (size_t)kTmaStages * kStageBytes + sizeof(SharedAcc<C::K>) + 64;
+};
+
+template <class C, class W2>
+__device__ __forceinline__ void run_planes_tma(const LagrangianParams& p, const W2& w2, SharedAcc<C::K>& sacc, unsigned char* stage_mem,
+                                               unsigned long long* bars) {
+  using L = TmaLayout<C>;
+  const long long B = p.batch;
+  const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
+  const int tid = threadIdx.x;
+  const unsigned bar0 = smem_u32(bars);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {      // thread 0 only
+    const long long b0 = tile * kTmaTile;
+    const long long left = B - b0;
+    const unsigned bytes = (unsigned)((left < kTmaTile ? left : kTmaTile) * 4);   // multiple of 16: the API requires B % 4 == 0
+    const unsigned bar = bar0 + 8 * stage;
+    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
+    mbar_expect_tx(bar, bytes * L::kPlanes);
+    int pl = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.theta + j * p.th_sj + b0, bytes, bar);
+#pragma unroll
+    for (int c = 0; c < 2; ++c, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.target + c * p.tg_sc + b0, bytes, bar);
+    if (C::DYN) {
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.obst + k * p.ob_so + c * p.ob_sc + b0, bytes, bar);
+      }
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+
+  f2 acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  int since_flush = 0, it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it % kTmaStages;
+    const unsigned parity = (unsigned)(it / kTmaStages) & 1u;
+    mbar_wait(bar0 + 8 * stage, parity);
+    const long long b = tile * kTmaTile + 2 * tid;
+    if (b < B) {
+      const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + 8 * tid;
+      f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+      int pl = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaPlaneBytes);
+      const f2 tx = *reinterpret_cast<const f2*>(base + 3 * kTmaPlaneBytes);
+      const f2 ty = *reinterpret_cast<const f2*>(base + 4 * kTmaPlaneBytes);
+      pl = 5;
+      if (C::DYN) {
+#pragma unroll
+        for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c, ++pl) ob[k][c] = *reinterpret_cast<const f2*>(base + pl * kTmaPlaneBytes);
+        }
+      } else {
+        static_obstacles_packed<C>(p, ob);
+      }
+      eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+      if (C::GRAD) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
+      } else {
+        store_side_outputs(p, b, b + 1, ee, tx, ty);
+      }
+    }
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      sacc.flush(acc);
+    }
+    __syncthreads();                                  // every thread is done reading this stage
+    const long long next = tile + (long long)kTmaStages * gridDim.x;
+    if (tid == 0 && next < ntiles) issue(next, stage);
+  }
+  sacc.flush(acc);
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  using L = TmaLayout<C>;
+  unsigned char* stage_mem = dyn_smem;
+  SharedAcc<C::K>& sacc = *reinterpret_cast<SharedAcc<C::K>*>(dyn_smem + (size_t)kTmaStages * L::kStageBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)kTmaStages * L::kStageBytes + sizeof(SharedAcc<C::K>));
+  __shared__ float2 s_lam2[kMaxK];
+  sacc.clear();
+  if constexpr (C::MODE == kGradDevW) {
+    if (threadIdx.x < C::K) {
+      const float l = __ldg(p.w_dev + threadIdx.x);
+      s_lam2[threadIdx.x] = make_float2(l, l);
+    }
+    __syncthreads();
+    const PackedSmemWeights w2{s_lam2};
+    run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
+  } else {
+    const PackedHostWeights w2{p.pu};
+    run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
+  }
+  finalize_sums<C::K>(p, sacc);
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
   __shared__ SharedAcc<C::K> sacc;
@@ -451,6 +606,29 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(co
 // ---- host-side launch ------------------------------------------------------------------------------------------
 template <class C>
 cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks, const char* name) {
+  if constexpr (C::LAYOUT == kPlanes) {
+    if (p.use_tma) {
+      static int tma_blocks_per_sm = 0;
+      constexpr size_t smem = TmaLayout<C>::kSmemBytes;
+      if (tma_blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(lagrangian_planes_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_planes_tma_kernel<C>, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        tma_blocks_per_sm = n > 0 ? n : 1;
+      }
+      long long tiles = (p.batch + kTmaTile - 1) / kTmaTile;
+      if (tiles < 1) tiles = 1;
+      long long grid = (long long)sm_count() * tma_blocks_per_sm;
+      if (grid > tiles) grid = tiles;
+      if (grid > max_blocks) grid = max_blocks;
+      set_last_kernel_name(name);
+      count_launch();
+      lagrangian_planes_tma_kernel<C><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
   static int blocks_per_sm = 0;      // per instantiation; same answer on every device of a homogeneous node
   if (blocks_per_sm == 0) {
     int n = 0;
