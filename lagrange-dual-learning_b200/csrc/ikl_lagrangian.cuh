@@ -109,19 +109,12 @@ struct SharedAcc {
   }
 };
 
+// Block-level tail shared by every kernel: s_red[warp][i] holds each warp's fp64 sum of constraint i.
 template <int K>
-__device__ __forceinline__ void finalize_sums(const LagrangianParams& p, SharedAcc<K>& sacc) {
-  __shared__ double s_red[kWarps][kMaxK];
+__device__ __forceinline__ void block_finalize(const LagrangianParams& p, double (*s_red)[kMaxK]) {
   __shared__ double s_fin[kFinalParts][kMaxK];
   __shared__ bool s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    double v = sacc.v[i][tid];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) s_red[warp][i] = v;
-  }
+  const int tid = threadIdx.x;
   __syncthreads();
   if (tid < K) {
     double v = 0.0;
@@ -160,6 +153,55 @@ __device__ __forceinline__ void finalize_sums(const LagrangianParams& p, SharedA
     *p.counter = 0u;            // leave the workspace ready for the next launch
   }
 }
+
+template <int K>
+__device__ __forceinline__ void finalize_sums(const LagrangianParams& p, SharedAcc<K>& sacc) {
+  __shared__ double s_red[kWarps][kMaxK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double v = sacc.v[i][tid];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][i] = v;
+  }
+  block_finalize<K>(p, s_red);
+}
+
+// Register-resident second level for the bulk-async kernel (its shared memory goes to the staging buffers):
+// level 0 = packed fp32 running sums (<= 64 samples), level 1 = K fp32 registers (<= 64 level-0 flushes), level 2 =
+// one fp64 slot per (warp, constraint) in shared memory, reached through a warp-shuffle reduction every 4096 samples.
+template <int K>
+struct WarpAcc {
+  double (*s_warp)[kMaxK];
+  float acc1[K];
+  int n1;
+  __device__ __forceinline__ explicit WarpAcc(double (*sw)[kMaxK]) : s_warp(sw), n1(0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc1[i] = 0.f;
+    if (threadIdx.x < kWarps * kMaxK) (&sw[0][0])[threadIdx.x] = 0.0;
+  }
+  __device__ __forceinline__ void deep_flush() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double v = (double)acc1[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) s_warp[warp][i] += v;
+      acc1[i] = 0.f;
+    }
+    n1 = 0;
+  }
+  __device__ __forceinline__ void flush(f2 (&acc)[K]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      acc1[i] += f2_lo(acc[i]) + f2_hi(acc[i]);
+      acc[i] = f2_splat(0.f);
+    }
+    if (++n1 == 64) deep_flush();
+  }
+};
 
 // ---- per-sample IO for the one-sample-per-thread layouts ----------------------------------------------------
 template <class C>
@@ -417,7 +459,7 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
 // per-plane address arithmetic, no long-scoreboard stalls) and write d/dtheta straight to HBM.  Two stages: tile k+1
 // is in flight while tile k is evaluated.
 constexpr int kTmaTile = 2 * kThreads;                 // samples per tile
-constexpr int kTmaStages = 2;
+
 constexpr int kTmaPlaneBytes = kTmaTile * 4;           // 2048
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -443,17 +485,24 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "r"(bytes), "r"(bar) : "memory");
 }
 
+// Measured on B200 (profiles/r01/kernel_table_v3_tma*.jsonl): the gradient kernel is register-bound, so it keeps its
+// fp64 second-level sums in shared memory (SharedAcc) and stages two tiles; the forward kernel has registers to spare,
+// keeps them in registers (WarpAcc) and spends the shared memory on a third stage.
 template <class C>
 struct TmaLayout {
   static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
   static constexpr int kStageBytes = kPlanes * kTmaPlaneBytes;
-  static constexpr size_t kSmemBytes = (size_t)kTmaStages * kStageBytes + sizeof(SharedAcc<C::K>) + 64;
+  static constexpr bool kSharedAcc = C::GRAD;
+  static constexpr int kStages = C::GRAD ? 2 : 3;
+  static constexpr size_t kAccBytes = kSharedAcc ? sizeof(SharedAcc<C::K>) : 0;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAccBytes + 64;
 };
 
-template <class C, class W2>
-__device__ __forceinline__ void run_planes_tma(const LagrangianParams& p, const W2& w2, SharedAcc<C::K>& sacc, unsigned char* stage_mem,
+template <class C, class W2, class Acc>
+__device__ __forceinline__ void run_planes_tma(const LagrangianParams& p, const W2& w2, Acc& sacc, unsigned char* stage_mem,
                                                unsigned long long* bars) {
   using L = TmaLayout<C>;
+  constexpr int kTmaStages = L::kStages;
   const long long B = p.batch;
   const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
   const int tid = threadIdx.x;
@@ -545,23 +594,36 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   using L = TmaLayout<C>;
   unsigned char* stage_mem = dyn_smem;
-  SharedAcc<C::K>& sacc = *reinterpret_cast<SharedAcc<C::K>*>(dyn_smem + (size_t)kTmaStages * L::kStageBytes);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)kTmaStages * L::kStageBytes + sizeof(SharedAcc<C::K>));
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes + L::kAccBytes);
   __shared__ float2 s_lam2[kMaxK];
-  sacc.clear();
+  __shared__ double s_warp[kWarps][kMaxK];
   if constexpr (C::MODE == kGradDevW) {
     if (threadIdx.x < C::K) {
       const float l = __ldg(p.w_dev + threadIdx.x);
       s_lam2[threadIdx.x] = make_float2(l, l);
     }
     __syncthreads();
-    const PackedSmemWeights w2{s_lam2};
-    run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
-  } else {
-    const PackedHostWeights w2{p.pu};
-    run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
   }
-  finalize_sums<C::K>(p, sacc);
+  auto run = [&](auto& sacc) {
+    if constexpr (C::MODE == kGradDevW) {
+      const PackedSmemWeights w2{s_lam2};
+      run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
+    } else {
+      const PackedHostWeights w2{p.pu};
+      run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
+    }
+  };
+  if constexpr (L::kSharedAcc) {
+    SharedAcc<C::K>& sacc = *reinterpret_cast<SharedAcc<C::K>*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
+    sacc.clear();
+    run(sacc);
+    finalize_sums<C::K>(p, sacc);
+  } else {
+    WarpAcc<C::K> sacc(s_warp);
+    run(sacc);
+    sacc.deep_flush();
+    block_finalize<C::K>(p, s_warp);
+  }
 }
 
 template <class C>
