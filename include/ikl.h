@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IKL_ABI_VERSION 1
+#define IKL_ABI_VERSION 2
 #define IKL_MAX_LINKS 3        /* reference trainer supports 3 (scripts/trainer.py:177-180); 2 is templated too */
 #define IKL_MAX_OBSTACLES 4    /* reference hard-wires (B,4,4): scripts/trainer.py:218, kinematics/dataset.py:80 */
 #define IKL_MAX_CONSTRAINTS (1 + IKL_MAX_LINKS + IKL_MAX_LINKS * IKL_MAX_OBSTACLES)   /* 16 */
@@ -73,8 +73,10 @@ int32_t ikl_num_constraints(const IklSpec* spec);
  * Native layouts (vectorised, no re-layout pass):
  *   "rows"   the reference's own tensors: theta (B,J) contiguous, target (B,3) contiguous,
  *            obstacles (B,4,4) contiguous [x, y, r, pad]   (kinematics/dataset.py:80-85,143-155)
- *   "planes" structure-of-arrays: every column its own contiguous plane of B floats with B % 4 == 0
- *            and 16-byte aligned planes (theta_sb == 1, theta_sj == plane pitch, ...).
+ *   "planes" structure-of-arrays: every column its own contiguous plane of B floats (theta_sb == 1,
+ *            theta_sj == plane pitch, ...).  Even B, 8-byte aligned planes and even pitches select the
+ *            packed kernel; B % 4 == 0 with 16-byte aligned planes and pitches % 4 == 0 select the
+ *            bulk-async (TMA) staged kernel, the fastest path.
  */
 typedef struct IklBatch {
   int64_t batch;                                   /* B >= 0 */
@@ -164,6 +166,27 @@ IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, cons
                                            const float* hi, int64_t s_hi, int64_t n,
                                            float inside_slope, float outside_slope, const float* grad_out,
                                            float* d_theta, float* d_lo, float* d_hi, void* stream);
+
+/* ---- the callers either side of the path, on the device ------------------------------------------ */
+
+/* kinematics/dataset.py:52-121 IkDataset.initialize, for 3-link arms: uniform joint angles inside the limits, FK
+ * for the targets, rejection sampling of dynamic obstacle centres in [-1.2, 1.2]^2 (dataset.py:98-104) or of the
+ * joint angles against static obstacles (dataset.py:109-121), collision rule of kinematics/penalties.py:75-92.
+ * One Philox stream per example: the output depends only on (seed, example index), not on the launch geometry.
+ * It has the reference's distribution, not its torch-CPU random stream (kinematics.dataset.IkDataset reproduces
+ * that one exactly, on the host).
+ *   theta_out (n,3), ee_out (n,3) = (x, y, phi); obstacles_out (n,4,4) rows [x, y, radius, 0] for dynamic configs
+ *   (NULL otherwise); exhausted_out: device counter (zeroed by the caller) of examples that gave up after 100000
+ *   re-draws (an obstacle covering the arm base loops forever in the reference). */
+IklStatus ikl_dataset_generate(const IklSpec* spec, int64_t n, uint64_t seed, float dynamic_radius, float* theta_out,
+                               float* ee_out, float* obstacles_out, uint32_t* exhausted_out, void* stream);
+
+/* scripts/evaluation/visualize_ik_solutions.py:97-119 on the device: over the per-sample constraint terms of a batch,
+ * counts_out[i] (i < K) += #(term_i > threshold) (the reference uses 1e-4); counts_out[16] += #samples with any
+ * joint-limit term > 0; counts_out[17] += #samples with any obstacle term > 0; pos_err_sum_out += sum over samples of
+ * sqrt(sum(position_err_sq)).  counts_out: 18 uint64 on the device, accumulated across calls (zero them first). */
+IklStatus ikl_eval_stats(const IklSpec* spec, const IklBatch* in, float threshold, uint64_t* counts_out,
+                         double* pos_err_sum_out, void* stream);
 
 /* ---- housekeeping ------------------------------------------------------------------------------ */
 int32_t ikl_abi_version(void);

@@ -15,7 +15,7 @@ _c_vp = ctypes.c_void_p
 MAX_LINKS = 3
 MAX_OBSTACLES = 4
 MAX_CONSTRAINTS = 1 + MAX_LINKS + MAX_LINKS * MAX_OBSTACLES
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 IKL_OK, IKL_ERR_INVALID_ARGUMENT, IKL_ERR_UNSUPPORTED, IKL_ERR_CUDA = 0, 1, 2, 3
 
@@ -57,6 +57,8 @@ _SIGNATURES = {
     "ikl_circle_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 5 + [_c_i64, _c_f, _c_f, _c_vp] + [_c_vp] * 5 + [_c_vp]),
     "ikl_joint_limit_penalty_forward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp, _c_vp]),
     "ikl_joint_limit_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp] + [_c_vp] * 3 + [_c_vp]),
+    "ikl_dataset_generate": (ctypes.c_int, [ctypes.POINTER(IklSpec), _c_i64, ctypes.c_uint64, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "ikl_eval_stats": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), _c_f, _c_vp, _c_vp, _c_vp]),
     "ikl_abi_version": (_c_i32, []),
     "ikl_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "ikl_last_cuda_error": (_c_i32, []),

@@ -106,6 +106,17 @@ class IkDataset(Dataset):
     self.N = self.random_theta.shape[0]
     return self
 
+  @classmethod
+  def generate_on_device(cls, N, J, config, seed=0, device=None):
+    """Benchmark-scale generation in one kernel launch (ikl_dataset_generate): same procedure and distribution as
+    initialize(), Philox instead of torch's CPU stream, tensors stay on the GPU."""
+    from ikl.device_data import generate_dataset
+    assert J == 3
+    tensors = generate_dataset(config, N, seed=seed, device=device, num_links=J)
+    if int(tensors["exhausted"].item()) != 0:
+      raise RuntimeError("dataset generation gave up on %d examples (an obstacle covers the arm base?)" % int(tensors["exhausted"].item()))
+    return cls.from_tensors(config, tensors, J=J)
+
   # -- generation --------------------------------------------------------------------------------------------------
   def initialize(self, N, J, config, seed=0):
     torch.manual_seed(seed)

@@ -162,3 +162,85 @@ def test_trainer_main_runs_and_writes_the_reference_artifacts(tmp_path, cuda_dev
   assert torch.equal(tr2.lambda_multipliers.cpu(), saved)
   for a, b in zip(tr.model.parameters(), tr2.model.parameters()):
     assert torch.equal(a, b)
+
+
+# ---- device-side dataset generation and evaluation statistics -----------------------------------
+@pytest.mark.parametrize("name", ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static", "cfg_joint_limits"))
+def test_device_dataset_generation(name, cuda_device):
+  from kinematics.dataset import IkDataset
+  from kinematics.forward_kinematics import ForwardKinematicsThreeLinkTorch
+  cfg = config_json(name)
+  N = 1 << 16
+  ds = IkDataset.generate_on_device(N, 3, cfg, seed=7)
+  assert ds.random_theta.is_cuda and len(ds) == N
+  lo, hi = cfg["static_constraints"]["joint_limits"]
+  th = ds.random_theta
+  assert float(th.min()) >= lo and float(th.max()) < hi
+  tips = ForwardKinematicsThreeLinkTorch(th)
+  assert torch.equal(ds.random_ee, tips[0]), "targets are the FK of the generated angles"
+  # uniform angles (only the dynamic/unconstrained configs keep the raw uniform draw)
+  if not cfg["static_constraints"]["obstacles"]:
+    assert abs(float(th.mean())) < 0.02 and abs(float(th.var()) - (hi - lo) ** 2 / 12) < 0.03
+  if ds.random_obstacles is not None:
+    ob = ds.random_obstacles
+    assert float(ob[:, :, :2].abs().max()) < 1.2 and torch.all(ob[:, :, 2] == 0.4) and torch.all(ob[:, :, 3] == 0)
+    for o in range(4):
+      for t in tips:
+        d = torch.sqrt((t[:, 0] - ob[:, o, 0]) ** 2 + (t[:, 1] - ob[:, o, 1]) ** 2)
+        assert float(d.min()) > 0.4, "no joint tip inside an obstacle"
+      assert float(torch.sqrt(ob[:, o, 0] ** 2 + ob[:, o, 1] ** 2).min()) > 0.4, "arm base outside every obstacle"
+  else:
+    # static: the last obstacle checked is always cleared (earlier ones may not be: the reference's rule)
+    obs = cfg["static_constraints"]["obstacles"]
+    if obs:
+      last = obs[-1]
+      for t in tips:
+        assert float(torch.sqrt((t[:, 0] - last["x"]) ** 2 + (t[:, 1] - last["y"]) ** 2).min()) > last["radius"]
+  # deterministic, and a function of (seed, index) only
+  again = IkDataset.generate_on_device(N, 3, cfg, seed=7)
+  assert torch.equal(again.random_theta, ds.random_theta)
+  prefix = IkDataset.generate_on_device(1000, 3, cfg, seed=7)
+  assert torch.equal(prefix.random_theta, ds.random_theta[:1000])
+  other = IkDataset.generate_on_device(1000, 3, cfg, seed=8)
+  assert not torch.equal(other.random_theta, prefix.random_theta)
+  item = ds[5]
+  assert item["input_tensor"].shape == (20,) and torch.equal(item["input_tensor"][:2], ds.random_ee[5, :2])
+
+
+def test_device_dataset_matches_host_generator_statistically(cuda_device):
+  """Same procedure, different random stream: first and second moments of the accepted obstacle centres agree."""
+  from kinematics.dataset import IkDataset
+  cfg = config_json("cfg_joint_limits_and_4obs_dynamic")
+  host = IkDataset(4000, 3, cfg, seed=1)
+  dev = IkDataset.generate_on_device(1 << 17, 3, cfg, seed=1)
+  h, d = host.random_obstacles[:, :, :2].reshape(-1, 2), dev.random_obstacles[:, :, :2].reshape(-1, 2).cpu()
+  assert float((h.mean(0) - d.mean(0)).abs().max()) < 0.03
+  assert float((h.var(0) - d.var(0)).abs().max()) < 0.03
+  assert abs(float(h.norm(dim=1).mean()) - float(d.norm(dim=1).mean())) < 0.02
+
+
+def test_eval_stats_match_per_sample_oracle(cuda_device):
+  from ikl import ConstraintSpec, synthetic
+  from ikl.device_data import eval_stats
+  from oracle import ik_oracle as O
+  for name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_1obs_static", "cfg_no_constraints"):
+    cfg = config_json(name)
+    spec = ConstraintSpec.from_config(cfg, 3, 0.005, 1.0)
+    ospec = O.spec_from_json(cfg, 3, 0.005, 1.0)
+    theta, q_des, obst = synthetic.make_batch(5000, seed=31)
+    out = O.lagrangian(theta.double(), q_des.double(), torch.ones(spec.num_constraints).double(), ospec, obst.double(), per_sample=True)
+    terms = out["per_sample_terms"]
+    K = spec.num_constraints
+    counts, err = eval_stats(spec, theta.cuda(), q_des.cuda(), obst.cuda() if spec.dynamic else None)
+    counts = counts.cpu()
+    want = (terms > 1e-4).sum(dim=0)
+    assert int((counts[:K] - want).abs().max()) <= 2, (counts[:K], want)        # fp32 vs fp64 right at the threshold
+    names = O.constraint_names(ospec)
+    jl = [i for i, n in enumerate(names) if "JL" in n]
+    ob = [i for i, n in enumerate(names) if "OB" in n]
+    if jl:
+      assert abs(int(counts[16]) - int((terms[:, jl] > 0).any(dim=1).sum())) <= 2
+    if ob:
+      assert abs(int(counts[17]) - int((terms[:, ob] > 0).any(dim=1).sum())) <= 2
+    want_err = torch.sqrt(out["position_err_sq"].sum(dim=1)).sum()
+    assert abs(float(err) - float(want_err)) <= 1e-5 * float(want_err)
