@@ -186,6 +186,74 @@ def train_step_metric(args, spec, dev, world, lam):
           "exchange": "one flat all-reduce of [83203 gradients | 16 violation sums]" if world > 1 else "none"}
 
 
+def small_batch_train_metric(args, spec, dev, lam):
+  """The reference's own regime (batch 8, scripts/options.py:15): train steps/s eager and as one CUDA graph per step,
+  beside the reference-style CPU step (torch CPU network + oracle Lagrangian + autograd + Adam) on the host."""
+  import torch
+  from ikl import fused, synthetic
+  from ikl.graph_step import GraphedTrainStep
+  from models.simple_network import SimpleNetwork
+  from oracle import ik_oracle as O
+  from ikl import standard_config
+  B = 8
+  torch.manual_seed(7)
+  theta0, q_des, obst = synthetic.make_batch(B, seed=77, device=str(dev))
+  x = torch.zeros(B, 20, device=dev)
+  x[:, 0:2] = q_des[:, :2]
+  x[:, 2], x[:, 3] = -synthetic.LIMIT, synthetic.LIMIT
+  x[:, 4:] = obst.reshape(B, 16)
+  lam_dev = torch.tensor(lam, device=dev)
+  inputs = {"input_tensor": x, "q_ee_desired": q_des, "dynamic_obstacles": obst}
+  out = {"batch": B}
+
+  def timed(fn, n):
+    for _ in range(20):
+      fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return n / (e0.elapsed_time(e1) * 1e-3)
+
+  model = SimpleNetwork(20, 3, hidden_units=100, depth=8, dropout=0.05).to(dev)
+  opt = torch.optim.Adam(model.parameters(), lr=5e-5)
+
+  def eager():
+    theta = model(x)
+    viol, loss = fused.FusedIkLagrangian.apply(theta, q_des, obst, lam_dev, spec, lam)
+    model.zero_grad()
+    loss.backward()
+    opt.step()
+  out["eager_steps_per_s"] = timed(eager, 300)
+  gmodel = SimpleNetwork(20, 3, hidden_units=100, depth=8, dropout=0.05).to(dev)
+  gopt = torch.optim.Adam(gmodel.parameters(), lr=5e-5, capturable=True)
+  g = GraphedTrainStep(gmodel, gopt, spec, B, dev)
+  g.set_multipliers(lam_dev)
+  out["graph_steps_per_s"] = timed(lambda: g.step(inputs), 2000)
+  # the reference's way, on the host cores
+  cmodel = SimpleNetwork(20, 3, hidden_units=100, depth=8, dropout=0.05)
+  copt = torch.optim.Adam(cmodel.parameters(), lr=5e-5)
+  ospec = O.spec_from_json(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
+  cx, cq, cob, clam = x.cpu(), q_des.cpu(), obst.cpu(), torch.tensor(lam)
+
+  def cpu_step():
+    o = O.lagrangian(cmodel(cx), cq, clam, ospec, cob)
+    cmodel.zero_grad()
+    o["lagrange_loss"].backward()
+    copt.step()
+  for _ in range(10):
+    cpu_step()
+  t0 = time.perf_counter()
+  for _ in range(100):
+    cpu_step()
+  out["cpu_reference_steps_per_s"] = 100 / (time.perf_counter() - t0)
+  out["note"] = "batch 8 (the reference's default), SimpleNetwork H=100 depth 8, Adam; graph = one CUDA-graph replay per step"
+  return out
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -331,9 +399,14 @@ def run_ours(args):
   if not args.skip_train_step:
     train = train_step_metric(args, spec, dev, world, lam)
 
+  small = None
+  if not args.skip_train_step and rank == 0 and world == 1:
+    small = small_batch_train_metric(args, spec, dev, lam)
+
   if rank == 0:
     line["e2e"] = e2e
     line["train_step"] = train
+    line["train_step_batch8"] = small
     if not args.skip_cpu:
       sps, dtc, cores, Bc = cpu_oracle_samples_per_s(args.cpu_batch_log2, 5, 1)
       line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",

@@ -102,7 +102,9 @@ class IkLagrangeDualTrainer(object):
     self.device = torch.device(device if device != "cuda" else "cuda:%d" % torch.cuda.current_device())
     self.model = SimpleNetwork(20, self.opt.num_links, hidden_units=self.opt.hidden_units, depth=8, dropout=0.05).to(self.device)
     ikl_dist.broadcast_parameters(self.model)
-    self.optimizer = Adam(self.model.parameters(), lr=self.opt.optimizer_lr, betas=(0.9, 0.999))
+    self.use_graph = bool(getattr(self.opt, "cuda_graph", False)) and self.world == 1 and self.device.type == "cuda"
+    self.optimizer = Adam(self.model.parameters(), lr=self.opt.optimizer_lr, betas=(0.9, 0.999), capturable=self.use_graph)
+    self._graph_step = None
 
     # constraint layout, names and lambda_0  (reference trainer.py:71-99)
     self.spec = ConstraintSpec.from_config(self.json_config, self.opt.num_links, self.opt.penalty_good_slope,
@@ -246,9 +248,17 @@ class IkLagrangeDualTrainer(object):
   # ---------------------------------------------------------------------------------------------------------------
   def train_with_relaxation(self, lamda):
     """One epoch of Adam steps on the Lagrangian relaxation with the multipliers held fixed (trainer.py:251-265)."""
+    if self.use_graph and self._graph_step is None:
+      from ikl.graph_step import GraphedTrainStep
+      self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size, self.device)
+    if self._graph_step is not None:
+      self._graph_step.set_multipliers(lamda)
     for ti, inputs in enumerate(self.train_loader):
       if ti >= self.opt.train_iters:
         break
+      if self._graph_step is not None and len(inputs["q_ee_desired"]) == self.opt.batch_size:
+        self._graph_step.step(inputs)          # the whole step (forward, Lagrangian, backward, Adam) is one graph replay
+        continue
       outputs = self.process_batch(inputs, lamda)
       self.model.zero_grad()
       outputs["lagrange_loss"].backward()

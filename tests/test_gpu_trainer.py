@@ -21,6 +21,7 @@ def make_trainer(name, tmp_path, fx, extra=()):
   from scripts.options import Options
   from scripts.trainer import IkLagrangeDualTrainer
   cfg = config_json(name)
+  os.makedirs(str(tmp_path), exist_ok=True)
   cfg_path = write_config(cfg, str(tmp_path / (name + ".json")))
   o = fx["opt"]
   argv = ["--model_name", "t", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--num_workers", "0"]
@@ -244,3 +245,24 @@ def test_eval_stats_match_per_sample_oracle(cuda_device):
       assert abs(int(counts[17]) - int((terms[:, ob] > 0).any(dim=1).sum())) <= 2
     want_err = torch.sqrt(out["position_err_sq"].sum(dim=1)).sum()
     assert abs(float(err) - float(want_err)) <= 1e-5 * float(want_err)
+
+
+def test_cuda_graph_train_step_matches_eager(tmp_path, cuda_device):
+  """--cuda_graph replays forward + fused Lagrangian + backward + Adam as one graph; same weights and lambda as eager."""
+  name = "cfg_joint_limits_and_4obs_dynamic"
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  eager = make_trainer(name, tmp_path / "eager", fx)
+  (tmp_path / "graph").mkdir()
+  graph = make_trainer(name, tmp_path / "graph", fx, extra=("--cuda_graph",))
+  graph.optimizer = torch.optim.Adam(graph.model.parameters(), lr=graph.opt.optimizer_lr, betas=(0.9, 0.999), capturable=True)
+  assert graph.use_graph
+  for tr in (eager, graph):
+    for _ in range(4):
+      tr.train_with_relaxation(tr.lambda_multipliers)
+      tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
+  assert graph._graph_step is not None
+  assert float((eager.lambda_multipliers - graph.lambda_multipliers).abs().max()) <= 1e-5 * float(eager.lambda_multipliers.abs().max())
+  for a, b in zip(eager.model.parameters(), graph.model.parameters()):
+    assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
+  hist = fx["lambda_history"]
+  assert float((graph.lambda_multipliers.cpu() - hist[4]).abs().max()) <= 2e-5 * float(hist[4].abs().max())
