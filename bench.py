@@ -268,7 +268,17 @@ def run_ours(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+      os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
+    opts = None
+    try:
+      opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    except Exception:
+      opts = None
+    dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    # optionally keep SMs out of the persistent grid for the concurrent NCCL kernel (measured: not needed on B200, the
+    # 64-byte all-reduce overlaps the next step's kernel either way: profiles/r01/bench_n2_*.json)
+    _cabi.set_reserved_sms(args.reserve_sms)
 
   spec = ConstraintSpec.from_config(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
   K = spec.num_constraints
@@ -283,11 +293,21 @@ def run_ours(args):
   accum = torch.zeros(K, dtype=torch.float64, device=dev)
   lam_dev = torch.tensor(lam, device=dev)
 
+  pending = []
+
   def step():
     viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta)
     if world > 1:
-      dist.all_reduce(viol)       # 16 floats: every rank sees the global sums that drive the multiplier update
+      # 16 floats: every rank sees the global sums that drive the multiplier update.  Asynchronous: NCCL's stream
+      # waits for this step's kernel, the compute stream does not wait for NCCL until drain().
+      pending.append((dist.all_reduce(viol, async_op=True), viol))
+      if len(pending) > 64:
+        pending.pop(0)[0].wait()
     return viol, loss
+
+  def drain():
+    while pending:
+      pending.pop(0)[0].wait()
 
   def barrier():
     if world > 1:
@@ -297,6 +317,7 @@ def run_ours(args):
   sampler = ClockSampler(local_rank) if rank == 0 else None
   for _ in range(max(args.warmup, 3)):
     step()
+  drain()
   barrier()
   launches0 = _cabi.launch_count()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,6 +325,7 @@ def run_ours(args):
   ev0.record()
   for _ in range(args.steps):
     viol, loss = step()
+  drain()                          # the timed region ends when every all-reduce has completed
   ev1.record()
   barrier()
   t_wall1 = time.time()
@@ -356,7 +378,7 @@ def run_ours(args):
         "config": {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
                    "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
                    "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
-                   "parallelism": "batch shard per GPU, all-reduce of 16 violation sums" if world > 1 else "single GPU"},
+                   "parallelism": "batch shard per GPU; asynchronous all-reduce of the 16 violation sums per step (overlaps the next step's kernel)" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
                      "peak_source": peak_src},
@@ -430,6 +452,7 @@ def main():
   ap.add_argument("--cpu-batch-log2", type=int, default=21)
   ap.add_argument("--train-batch-log2", type=int, default=20)
   ap.add_argument("--skip-train-step", action="store_true")
+  ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1 only: SMs left out of the persistent grid for the concurrent NCCL kernel")
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
   args = ap.parse_args()

@@ -192,6 +192,9 @@ IklStatus ikl_eval_stats(const IklSpec* spec, const IklBatch* in, float threshol
 int32_t ikl_abi_version(void);
 const char* ikl_strerror(IklStatus status);
 int32_t ikl_last_cuda_error(void);
+/* Leave `n` SMs out of the persistent grids of the Lagrangian kernels (default 0).  A multi-GPU caller sets 1 so that
+ * the tiny NCCL all-reduce of step k runs on the free SM while the kernel of step k+1 already occupies the others. */
+void ikl_set_reserved_sms(int32_t n);
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 int64_t ikl_launch_count(void);
 /* Name of the kernel variant the last ikl_lagrangian_* call on this thread dispatched to. */

@@ -14,6 +14,7 @@ namespace {
 thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 thread_local const char* g_last_kernel = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_reserved_sms{0};
 
 constexpr int kMaxGrid = 2048;                                       // upper bound on persistent grid size
 constexpr size_t kPartialsBytes = (size_t)kMaxGrid * kMaxK * sizeof(double);
@@ -23,6 +24,8 @@ constexpr size_t kWorkspaceBytes = kPartialsBytes + 256;             // + the co
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 void set_last_kernel_name(const char* name) { g_last_kernel = name; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int reserved_sms() { return g_reserved_sms.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -228,6 +231,8 @@ IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* i
 }
 
 int32_t ikl_abi_version(void) { return IKL_ABI_VERSION; }
+
+void ikl_set_reserved_sms(int32_t n) { g_reserved_sms.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
 
 const char* ikl_strerror(IklStatus status) {
   switch (status) {

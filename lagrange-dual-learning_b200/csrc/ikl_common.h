@@ -15,6 +15,8 @@ void count_launch(int n = 1);
 
 // SM count / of the current device, cached per device ordinal.
 int sm_count();
+// SMs the persistent Lagrangian grids leave free (ikl_set_reserved_sms), e.g. for a concurrent NCCL kernel.
+int reserved_sms();
 
 inline IklStatus cuda_status(cudaError_t e) {
   if (e == cudaSuccess) return IKL_OK;

@@ -666,6 +666,11 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(co
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------------------
+inline int grid_sms() {
+  const int n = sm_count() - reserved_sms();
+  return n > 0 ? n : 1;
+}
+
 template <class C>
 cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks, const char* name) {
   if constexpr (C::LAYOUT == kPlanes) {
@@ -682,7 +687,7 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       }
       long long tiles = (p.batch + kTmaTile - 1) / kTmaTile;
       if (tiles < 1) tiles = 1;
-      long long grid = (long long)sm_count() * tma_blocks_per_sm;
+      long long grid = (long long)grid_sms() * tma_blocks_per_sm;
       if (grid > tiles) grid = tiles;
       if (grid > max_blocks) grid = max_blocks;
       set_last_kernel_name(name);
@@ -701,7 +706,7 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
   const long long per_block = (long long)kThreads * (C::LAYOUT == kStrided ? IKL_ROWS_UNROLL : 2);
   long long tiles = (p.batch + per_block - 1) / per_block;
   if (tiles < 1) tiles = 1;
-  long long grid = (long long)sm_count() * blocks_per_sm;
+  long long grid = (long long)grid_sms() * blocks_per_sm;
   if (grid > tiles) grid = tiles;
   if (grid > max_blocks) grid = max_blocks;
   set_last_kernel_name(name);

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "ikl_joint_limit_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp] + [_c_vp] * 3 + [_c_vp]),
     "ikl_dataset_generate": (ctypes.c_int, [ctypes.POINTER(IklSpec), _c_i64, ctypes.c_uint64, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "ikl_eval_stats": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), _c_f, _c_vp, _c_vp, _c_vp]),
+    "ikl_set_reserved_sms": (None, [_c_i32]),
     "ikl_abi_version": (_c_i32, []),
     "ikl_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "ikl_last_cuda_error": (_c_i32, []),
@@ -118,6 +119,10 @@ def check(status, what):
   if status == IKL_ERR_CUDA:
     msg += " (cudaError %d)" % lib.ikl_last_cuda_error()
   raise RuntimeError("%s failed: %s" % (what, msg))
+
+
+def set_reserved_sms(n):
+  load().ikl_set_reserved_sms(int(n))
 
 
 def launch_count():
