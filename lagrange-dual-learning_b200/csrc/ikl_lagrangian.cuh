@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
     finalize_sums<C::K>(p, sacc);
   } else {
     WarpAcc<C::K> sacc(s_warp);
+    __syncthreads();                 // s_warp is zeroed by other warps' threads
     run(sacc);
     sacc.deep_flush();
     block_finalize<C::K>(p, s_warp);
