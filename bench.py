@@ -114,6 +114,26 @@ def cpu_oracle_samples_per_s(batch_log2, steps, warmup):
   return B / dt, dt, torch.get_num_threads(), B
 
 
+def cpu_c_oracle_samples_per_s(batch_log2):
+  """The plain-C / OpenMP restatement (oracle/ik_oracle.c, float arithmetic, closed-form gradient): what a tuned CPU port
+  of the same maths reaches on this host -- reported as context next to the reference-style PyTorch baseline."""
+  import numpy as np
+  from oracle import build_oracle as C, ik_oracle as O
+  from ikl import synthetic, standard_config
+  B = 1 << batch_log2
+  ospec = O.spec_from_json(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
+  theta, q_des, obst = (t.numpy() for t in synthetic.make_batch(B, seed=0))
+  lam = np.asarray(synthetic.SHIPPED_LAMBDA_OBS4_DYN, dtype=np.float32)
+  C.lagrangian_f32(ospec, theta, q_des, obst, lam)
+  best = 1e9
+  for _ in range(5):
+    t0 = time.perf_counter()
+    C.lagrangian_f32(ospec, theta, q_des, obst, lam)
+    best = min(best, time.perf_counter() - t0)
+  return {"value": B / best, "unit": UNIT, "cores": C.max_threads(), "kind": "port",
+          "sample": "oracle/ik_oracle.c (C + OpenMP, fp32 maths, closed-form gradient) on a 2^%d-sample batch, best of 5" % batch_log2}
+
+
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
@@ -434,6 +454,10 @@ def run_ours(args):
       line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
                               "sample": "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32) on a 2^%d-sample "
                                         "batch of the same workload, mean of 5 after 1 warm-up (%.0f ms each)" % (args.cpu_batch_log2, dtc * 1e3)}
+      try:
+        line["cpu_baseline_c"] = cpu_c_oracle_samples_per_s(args.cpu_batch_log2 + 1)
+      except Exception as e:          # no C compiler on the box: the PyTorch port above is the baseline of record
+        line["cpu_baseline_c"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()

@@ -171,3 +171,34 @@ def test_standard_configs_equal_reference_json_when_mounted():
   for p in glob.glob(os.path.join(ref, "cfg_*.json")):
     with open(p) as f:
       assert json.load(f) == config_json(os.path.basename(p)[:-5]), p
+
+
+# --- the C restatement (oracle/ik_oracle.c) against the pinned PyTorch oracle -------------------------------------------
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_c_oracle_agrees_with_pinned_torch_oracle(name):
+  from oracle import build_oracle as C
+  g = golden_npz("process_batch_%s.npz" % name)
+  spec = O.spec_from_json(config_json(name), 3, float(g["good_slope"]), float(g["bad_slope"]))
+  theta, q_des, obst, lam = g["theta"], g["q_ee_desired"], g["dynamic_obstacles"], g["lam_ramp"]
+  ref = O.lagrangian_with_grad(torch.from_numpy(theta).double(), torch.from_numpy(q_des).double(), torch.from_numpy(lam).double(), spec,
+                               torch.from_numpy(obst).double() if spec.dynamic else None)
+  sums, abs_sums, dth = C.lagrangian_f64(spec, theta, q_des, obst, lam)
+  np.testing.assert_allclose(sums, ref["constraint_violations"].numpy(), rtol=1e-12, atol=1e-12)
+  np.testing.assert_allclose(dth, ref["dtheta"].numpy(), rtol=1e-11, atol=1e-12)
+  assert np.all(abs_sums >= np.abs(sums) - 1e-12)
+  # float path against the reference's own fp32 trainer outputs
+  sums32, dth32 = C.lagrangian_f32(spec, theta, q_des, obst, lam)
+  np.testing.assert_allclose(sums32, g["viol_ramp"], rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(dth32, g["dtheta_ramp"], rtol=2e-5, atol=2e-5)
+
+
+def test_c_oracle_large_batch_and_threads():
+  from oracle import build_oracle as C
+  from ikl import synthetic
+  spec = O.spec_from_json(config_json("cfg_joint_limits_and_4obs_dynamic"), 3, 0.005, 1.0)
+  theta, q_des, obst = synthetic.make_batch(1 << 16, seed=3)
+  lam = np.linspace(0.5, 2.0, 16)
+  sums, abs_sums, dth = C.lagrangian_f64(spec, theta.numpy(), q_des.numpy(), obst.numpy(), lam)
+  ref = O.lagrangian(theta.double(), q_des.double(), torch.from_numpy(lam), spec, obst.double())
+  np.testing.assert_allclose(sums, ref["constraint_violations"].numpy(), rtol=1e-10)
+  assert C.max_threads() >= 1
