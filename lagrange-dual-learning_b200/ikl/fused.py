@@ -143,10 +143,11 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
   with torch.cuda.device(dev):
     out = torch.empty(K + 1, dtype=torch.float32, device=dev)
     if dtheta is None:
-      # same memory layout as theta when it is dense (rows or planes); otherwise row-major
-      dense = theta.is_contiguous() or theta.t().is_contiguous()
-      dtheta = torch.empty_strided(theta.shape, theta.stride(), dtype=torch.float32, device=dev) if dense else \
-          torch.empty(theta.shape, dtype=torch.float32, device=dev)
+      # planes in (theta.stride(0) == 1, possibly a slice of wider planes) -> planes out; otherwise row-major
+      if theta.dim() == 2 and theta.shape[0] > 1 and theta.stride(0) == 1:
+        dtheta = torch.empty(theta.shape[1], theta.shape[0], dtype=torch.float32, device=dev).t()
+      else:
+        dtheta = torch.empty(theta.shape, dtype=torch.float32, device=dev)
     else:
       _require_cuda_f32(dtheta, "dtheta")
       if dtheta.shape != theta.shape:

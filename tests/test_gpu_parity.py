@@ -504,3 +504,57 @@ def test_full_size_properties(cuda_device, monkeypatch):
     tot += o["constraint_violations"].numpy()
     tot_abs += o["per_sample_terms"].abs().sum(dim=0).numpy()
   assert np.all(np.abs(v1.cpu().numpy() - tot) <= RTOL * tot_abs)
+
+
+def test_layout_dispatch_on_views_and_alignments(cuda_device, monkeypatch):
+  """Slices, odd batch sizes and unaligned planes fall through to the next-best kernel and give the same numbers."""
+  from ikl import fused, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  dev = cuda_device
+  B = 4100
+  theta, q_des, obst = synthetic.make_batch(B, seed=17, device="cuda:0")
+  lam = [0.5 + 0.1 * i for i in range(16)]
+
+  def run(th, qd, ob):
+    v, l, d = fused.lagrangian_forward_backward(spec, th, qd, ob, lam)
+    return v.clone(), d.contiguous().clone(), _cabi.last_kernel_name()
+
+  v0, d0, k0 = run(theta, q_des, obst)
+  assert "<rows," in k0
+  # planes, multiple of 4 and aligned -> bulk-async kernel
+  thp, tgp, obp = synthetic.to_planes(theta, q_des, obst)
+  v1, d1, k1 = run(thp, tgp, obp)
+  scale = float(d0.abs().max())
+  tol = 2e-6 * scale
+
+  def near(a, b):
+    """scalar-maths vs packed-maths kernels: equal to fp32 round-off, except where a tip almost sits on an obstacle centre
+    and the 1/d amplification (see oracle_truth) applies -- a handful of samples, still within 1e-3 of the scale."""
+    err = (a - b).abs()
+    return float((err > tol).float().mean()) < 2e-3 and float(err.max()) <= 1e-3 * scale
+  # rows evaluates full 512-sample tiles with the packed maths and the ragged tail with the scalar maths: bit-identical
+  # to the all-packed planes kernels on the tiles, equal to round-off on the tail
+  assert "<planes_tma," in k1 and torch.equal(d1[:4096], d0[:4096]) and near(d1, d0)
+  # planes of an even but not 4-divisible batch -> direct 8-byte loads
+  n = B - 2
+  thp2, tgp2, obp2 = synthetic.to_planes(theta[:n], q_des[:n], obst[:n])
+  v2, d2, k2 = run(thp2, tgp2, obp2)
+  assert "<planes," in k2 and torch.equal(d2[:4096], d0[:4096]) and near(d2, d0[:n])
+  # plane views starting 8 bytes into their allocation (a slice along the batch) -> still the direct planes kernel
+  v3, d3, k3 = run(thp[2:], tgp[2:], obp[2:])
+  assert "<planes," in k3 and torch.equal(d3[:4094], d0[2:4096]) and near(d3, d0[2:])
+  # odd offset: 4-byte aligned only -> strided kernel, same sums to round-off
+  v4, d4, k4 = run(thp[1:-1], tgp[1:-1], obp[1:-1])
+  assert "<strided," in k4
+  assert near(d4, d0[1:-1])
+  # odd batch of rows: packed tiles + scalar tail
+  v5, d5, k5 = run(theta[:-1], q_des[:-1], obst[:-1])
+  assert "<rows," in k5 and torch.equal(d5[:4096 - 0], d0[:4096]) and near(d5, d0[:-1])
+  # q_ee_desired with only two columns, non-contiguous theta (every other row of a bigger tensor)
+  big = torch.zeros(2 * B, 3, device=dev)
+  big[::2] = theta
+  v6, d6, k6 = run(big[::2], q_des[:, :2], obst)
+  assert "<strided," in k6 and near(d6, d0)
+  sums = torch.stack([v0, v1, v6])
+  assert float((sums - v0).abs().max()) <= 1e-6 * float(v0.abs().max())
