@@ -407,6 +407,45 @@ def run_ours(args):
         "native_lib": _cabi.loaded_path(),
     }
 
+  # ---- context numbers (rank 0, N = 1): the reference's own tensor layout, and the reference's eager path on this GPU
+  extras = {}
+  if rank == 0 and world == 1 and not args.skip_context:
+    dth_rows = torch.empty_like(theta)
+    for _ in range(3):
+      fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam, dtheta=dth_rows)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(20):
+      fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam, dtheta=dth_rows)
+    r1.record()
+    torch.cuda.synchronize()
+    rows_ms = r0.elapsed_time(r1) / 20
+    extras["rows_layout"] = {"kernel": _cabi.last_kernel_name(), "kernel_ms": rows_ms, "samples_per_s": B / (rows_ms * 1e-3),
+                             "frac_of_hbm_peak_algorithmic": ALGO_BYTES_PER_SAMPLE * B / (rows_ms * 1e-3) / 1e9 / measured_peak()[0],
+                             "note": "theta (B,3), q_ee_desired (B,3), dynamic_obstacles (B,4,4) exactly as the reference's DataLoader "
+                                     "hands them: 100 physical bytes per sample"}
+    del dth_rows
+    try:
+      from oracle import ik_oracle as O
+      Bg = 1 << 22
+      ospec = O.spec_from_json(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
+      th_g, qd_g, ob_g = theta[:Bg].clone(), q_des[:Bg].clone(), obst[:Bg].clone()
+      O.lagrangian_with_grad(th_g, qd_g, lam_dev, ospec, ob_g)
+      torch.cuda.synchronize()
+      g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      g0.record()
+      for _ in range(3):
+        O.lagrangian_with_grad(th_g, qd_g, lam_dev, ospec, ob_g)
+      g1.record()
+      torch.cuda.synchronize()
+      eager_ms = g0.elapsed_time(g1) / 3
+      extras["reference_eager_cuda"] = {"samples_per_s": Bg / (eager_ms * 1e-3), "ms_per_step": eager_ms, "batch": Bg,
+                                        "note": "the reference's op-by-op PyTorch path (oracle port, ~960 eager kernels fwd+bwd) on this same GPU"}
+      del th_g, qd_g, ob_g
+      torch.cuda.empty_cache()
+    except Exception as e:
+      extras["reference_eager_cuda"] = {"unavailable": str(e)[:200]}
+
   # ---- end to end through the host-buffer API (rank-local; every rank does the same work) -------------------
   e2e = None
   if not args.skip_e2e:
@@ -449,7 +488,8 @@ def run_ours(args):
     line["e2e"] = e2e
     line["train_step"] = train
     line["train_step_batch8"] = small
-    if not args.skip_cpu:
+    line["context"] = extras
+    if not args.skip_cpu and world == 1:
       sps, dtc, cores, Bc = cpu_oracle_samples_per_s(args.cpu_batch_log2, 5, 1)
       line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
                               "sample": "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32) on a 2^%d-sample "
@@ -477,6 +517,7 @@ def main():
   ap.add_argument("--train-batch-log2", type=int, default=20)
   ap.add_argument("--skip-train-step", action="store_true")
   ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1 only: SMs left out of the persistent grid for the concurrent NCCL kernel")
+  ap.add_argument("--skip-context", action="store_true")
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
   args = ap.parse_args()
