@@ -193,7 +193,7 @@ def lagrangian(theta: torch.Tensor, q_ee_desired: torch.Tensor, lam: torch.Tenso
   cols = [err.sum(dim=1)] if per_sample else None
 
   if spec.enforce_joint_limits:                                    # trainer.py:198-205
-    lim = torch.tensor(spec.joint_limits, dtype=torch.float32).to(dt).unsqueeze(0).expand(B, -1)  # trainer.py:170
+    lim = torch.tensor(spec.joint_limits, dtype=torch.float32).to(dt).unsqueeze(0).expand(B, -1).to(theta.device)  # trainer.py:170
     jl = []
     for j in range(spec.num_links):
       pj = joint_limit_penalty(theta[:, j], lim[:, 0], lim[:, 1],
@@ -204,7 +204,7 @@ def lagrangian(theta: torch.Tensor, q_ee_desired: torch.Tensor, lam: torch.Tenso
     sums.append(torch.stack(jl))
 
   if spec.enforce_obstacles:                                       # trainer.py:209-241
-    obst = obstacle_table(spec, B, dynamic_obstacles, dt)
+    obst = obstacle_table(spec, B, dynamic_obstacles, dt).to(theta.device)
     ob = []
     for o in range(spec.num_obstacles):
       ox, oy, rad = obst[:, o, 0], obst[:, o, 1], obst[:, o, 2]
@@ -217,7 +217,7 @@ def lagrangian(theta: torch.Tensor, q_ee_desired: torch.Tensor, lam: torch.Tenso
     if ob:
       sums.append(torch.stack(ob))
     else:
-      sums.append(torch.zeros(0, dtype=dt))
+      sums.append(torch.zeros(0, dtype=dt, device=theta.device))
 
   viol = torch.cat(sums)                                           # trainer.py:244
   out["constraint_violations"] = viol
