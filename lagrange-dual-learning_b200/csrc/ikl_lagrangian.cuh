@@ -22,7 +22,10 @@
 
 namespace ikl {
 
-constexpr int kThreads = 256;
+#ifndef IKL_THREADS
+#define IKL_THREADS 256
+#endif
+constexpr int kThreads = IKL_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kFlushSamples = 64;   // samples a thread adds in fp32 before flushing into its fp64 slot in shared memory
 constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce

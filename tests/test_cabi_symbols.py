@@ -97,3 +97,25 @@ def test_reference_trainer_imports_against_dropin_tree_when_mounted():
     assert callable(getattr(fk, n))
   for n in ("piecewise_joint_limit_penalty", "piecewise_circle_penalty", "no_joint_collisions_circle", "no_joint_collisions_rectangle"):
     assert callable(getattr(pen, n))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+  """No silent fallback: pointing the binding at a library that is not there raises."""
+  monkeypatch.setenv("IKL_LIB", "/nonexistent/libikl.so")
+  monkeypatch.setattr(_cabi, "_lib", None)
+  monkeypatch.setattr(_cabi, "_lib_path", None)
+  with pytest.raises(RuntimeError):
+    _cabi.load()
+
+
+def test_product_tree_never_imports_the_oracle():
+  """oracle/ is test infrastructure: nothing under the package may reference it."""
+  pkg = os.path.join(ROOT, "lagrange-dual-learning_b200")
+  for base, _, files in os.walk(pkg):
+    if os.sep + "build" in base:
+      continue
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
+        text = open(os.path.join(base, f), errors="ignore").read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(base, f)
+        assert "ik_oracle" not in text, os.path.join(base, f)
