@@ -558,3 +558,41 @@ def test_layout_dispatch_on_views_and_alignments(cuda_device, monkeypatch):
   assert "<strided," in k6 and near(d6, d0)
   sums = torch.stack([v0, v1, v6])
   assert float((sums - v0).abs().max()) <= 1e-6 * float(v0.abs().max())
+
+
+@pytest.mark.parametrize("J,lengths", [(2, (1.0, 1.0)), (3, (0.7, 1.3, 0.45)), (2, (0.5, 1.5))])
+def test_two_links_and_non_unit_link_lengths(J, lengths, cuda_device):
+  """The strided kernel family: 2-link arms (reference: only the NumPy FK, forward_kinematics.py:7-22) and runtime link
+  lengths (utils/constants.py holds them as constants), against the oracle evaluated with the same geometry."""
+  import dataclasses
+  from ikl import ConstraintSpec, fused, _cabi
+  cfg = config_json("cfg_joint_limits_and_4obs_dynamic")
+  spec = ConstraintSpec.from_config(cfg, J, 0.005, 1.0, link_lengths=lengths)
+  ospec = dataclasses.replace(O.spec_from_json(cfg, J, 0.005, 1.0), link_lengths=tuple(lengths))
+  K = spec.num_constraints
+  assert K == 1 + J + 4 * J == ospec.num_constraints
+  g = torch.Generator().manual_seed(40 + J)
+  B = 3000
+  theta = (torch.rand(B, J, generator=g) * 2 - 1) * 2.5
+  q_des = torch.cat([(torch.rand(B, 2, generator=g) * 2 - 1) * sum(lengths), torch.zeros(B, 1)], dim=1)
+  obst = torch.zeros(B, 4, 4)
+  obst[:, :, :2] = (torch.rand(B, 4, 2, generator=g) * 2 - 1) * 1.2
+  obst[:, :, 2] = 0.4
+  lam = np.linspace(0.4, 1.9, K).astype(np.float32)
+  ref = O.lagrangian(theta.double(), q_des.double(), torch.from_numpy(lam).double(), ospec, obst.double(), per_sample=True)
+  sums64 = ref["constraint_violations"].numpy()
+  abs_sums = ref["per_sample_terms"].abs().sum(dim=0).numpy()
+  _, dth64 = O.lagrangian_grad_closed_form(theta.numpy(), q_des.numpy(), lam, ospec, obst.numpy())
+  dev = cuda_device
+  viol, loss, dth = fused.lagrangian_forward_backward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam.tolist())
+  assert "<strided,J%d" % J in _cabi.last_kernel_name()
+  assert np.all(np.abs(viol.cpu().numpy() - sums64) <= RTOL * abs_sums)
+  err = np.abs(dth.cpu().numpy() - dth64).max(axis=1)
+  scale = np.abs(dth64).max()
+  assert (err > RTOL * scale).mean() < 3e-3 and err.max() < 1e-3 * scale      # see oracle_truth on conditioning
+  # forward-only launch and the function-level FK agree with the same geometry
+  out = fused.lagrangian_forward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam.tolist(), want_q_ee=(J == 3))
+  assert np.array_equal(out["constraint_violations"].cpu().numpy(), viol.cpu().numpy())
+  from ikl import ops
+  tips = ops.fk_forward_kinematics(theta.to(dev), lengths)
+  close(tips[0].cpu().numpy(), O.forward_kinematics(theta.double(), lengths)[0].numpy(), scale=sum(lengths))
