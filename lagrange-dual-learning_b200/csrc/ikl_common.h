@@ -24,10 +24,5 @@ inline IklStatus cuda_status(cudaError_t e) {
   return IKL_ERR_CUDA;
 }
 
-#define IKL_CUDA_TRY(expr)                                   \
-  do {                                                       \
-    cudaError_t _e = (expr);                                 \
-    if (_e != cudaSuccess) return ::ikl::cuda_status(_e);    \
-  } while (0)
 
 }  // namespace ikl

@@ -30,9 +30,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kFlushSamples = 64;   // samples a thread adds in fp32 before flushing into its fp64 slot in shared memory
 constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce
 
-#ifndef IKL_PLANES_VEC
-#define IKL_PLANES_VEC 2          // samples per thread per iteration in the planes layout (the packed pair)
-#endif
 #ifndef IKL_ROWS_UNROLL
 #define IKL_ROWS_UNROLL 2         // samples in flight per thread in the strided fallback
 #endif
@@ -73,11 +70,6 @@ struct Cfg {
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float2 ldg_stream2(const float* p) {
-  float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float ldg_stream1(const float* p) {
