@@ -266,3 +266,32 @@ def test_cuda_graph_train_step_matches_eager(tmp_path, cuda_device):
     assert float((a - b).detach().abs().max()) <= 2e-5 * max(1.0, float(a.detach().abs().max()))
   hist = fx["lambda_history"]
   assert float((graph.lambda_multipliers.cpu() - hist[4]).abs().max()) <= 2e-5 * float(hist[4].abs().max())
+
+
+def test_evaluation_script_matches_per_example_loop(tmp_path, cuda_device):
+  """scripts/evaluation/evaluate_ik_solutions.py against the reference's procedure (visualize_ik_solutions.py:53-119):
+  one example at a time through process_batch, thresholds on the host."""
+  from scripts.evaluation.evaluate_ik_solutions import evaluate
+  name = "cfg_joint_limits_and_4obs_dynamic"
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  tr = make_trainer(name, tmp_path, fx)
+  tr.model.load_state_dict(fx["final_state"])
+  stats = evaluate(tr, batch_size=16)
+  tr.model.eval()
+  pos, viol = [], []
+  with torch.no_grad():
+    for i in range(len(tr.val_dataset)):
+      inputs = {k: v.unsqueeze(0) for k, v in tr.val_dataset[i].items()}
+      out = tr.process_batch_unfused(inputs, tr.lambda_multipliers)
+      pos.append(torch.sqrt(out["position_err_sq"].sum()).unsqueeze(0))
+      viol.append(out["constraint_violations"].unsqueeze(0))
+  viol = torch.cat(viol).cpu()
+  want_counts = (viol > 1e-4).sum(dim=0)
+  names = tr.constraint_names
+  jl = [i for i, n in enumerate(names) if "JL" in n]
+  ob = [i for i, n in enumerate(names) if "OB" in n]
+  assert stats["n"] == 32
+  assert stats["num_violations"] == want_counts.tolist()
+  assert stats["any_joint_limit"] == int(((viol[:, jl] > 0).sum(dim=1) > 0).sum())
+  assert stats["any_obstacle"] == int(((viol[:, ob] > 0).sum(dim=1) > 0).sum())
+  assert abs(stats["position_err"] - float(torch.cat(pos).mean())) <= 1e-5 * float(torch.cat(pos).mean())
