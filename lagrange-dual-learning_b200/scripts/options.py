@@ -41,6 +41,8 @@ class Options(object):
     # Additions of the B200 implementation.
     self.parser.add_argument("--unfused", action="store_true", default=False,
                              help="process_batch goes op by op through the function-level CUDA drop-ins instead of the fused kernel")
+    self.parser.add_argument("--device_data", action="store_true", default=False,
+                             help="Generate the datasets on the GPU and batch them there (for large batch sizes)")
     self.parser.add_argument("--cuda_graph", action="store_true", default=False,
                              help="Replay each train step (network, fused Lagrangian, backward, Adam) as one CUDA graph")
     self.parser.add_argument("--load_multipliers", action="store_true", default=False,

@@ -153,6 +153,12 @@ class IkLagrangeDualTrainer(object):
 
     if datasets is not None:
       self.train_dataset, self.val_dataset = datasets
+    elif getattr(self.opt, "device_data", False):
+      # benchmark-scale path: generate on the GPU (one kernel launch), keep everything device-resident
+      self.train_dataset = IkDataset.generate_on_device(self.opt.train_dataset_size, self.opt.num_links, self.json_config, seed=0,
+                                                        device=self.device)
+      self.val_dataset = IkDataset.generate_on_device(self.opt.val_dataset_size, self.opt.num_links, self.json_config, seed=1,
+                                                      device=self.device)
     else:
       train_cache = val_cache = None
       if self.opt.cache_save_path is not None:
@@ -161,8 +167,13 @@ class IkLagrangeDualTrainer(object):
       self.train_dataset = IkDataset(self.opt.train_dataset_size, self.opt.num_links, self.json_config, cache_save_path=train_cache)
       self.val_dataset = IkDataset(self.opt.val_dataset_size, self.opt.num_links, self.json_config, cache_save_path=val_cache)
 
-    self.train_loader = ikl_dist.make_loader(self.train_dataset, self.opt.batch_size, self.opt.num_workers)
-    self.val_loader = ikl_dist.make_loader(self.val_dataset, self.opt.batch_size, self.opt.num_workers)
+    if getattr(self.opt, "device_data", False):
+      from ikl.device_loader import DeviceBatchLoader
+      self.train_loader = DeviceBatchLoader(self.train_dataset, self.opt.batch_size, True, device=self.device, seed=11)
+      self.val_loader = DeviceBatchLoader(self.val_dataset, self.opt.batch_size, True, device=self.device, seed=12)
+    else:
+      self.train_loader = ikl_dist.make_loader(self.train_dataset, self.opt.batch_size, self.opt.num_workers)
+      self.val_loader = ikl_dist.make_loader(self.val_dataset, self.opt.batch_size, self.opt.num_workers)
 
   # ---------------------------------------------------------------------------------------------------------------
   def _host_multipliers(self, lamda):

@@ -295,3 +295,23 @@ def test_evaluation_script_matches_per_example_loop(tmp_path, cuda_device):
   assert stats["any_joint_limit"] == int(((viol[:, jl] > 0).sum(dim=1) > 0).sum())
   assert stats["any_obstacle"] == int(((viol[:, ob] > 0).sum(dim=1) > 0).sum())
   assert abs(stats["position_err"] - float(torch.cat(pos).mean())) <= 1e-5 * float(torch.cat(pos).mean())
+
+
+def test_trainer_with_device_resident_data(tmp_path, cuda_device):
+  """--device_data: datasets generated on the GPU, batches assembled there; main() runs with a large batch and lambda moves."""
+  from ikl.configs import write_config
+  from scripts.options import Options
+  from scripts.trainer import IkLagrangeDualTrainer
+  cfg_path = write_config(config_json("cfg_joint_limits_and_4obs_dynamic"), str(tmp_path / "cfg.json"))
+  opt = Options().parse(["--model_name", "dev", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--device_data",
+                         "--train_dataset_size", "65536", "--val_dataset_size", "16384", "--batch_size", "8192", "--lagrange_iters", "2",
+                         "--train_iters", "8", "--hidden_units", "32", "--initial_lambda", "1", "--penalty_good_slope", "0.005",
+                         "--model_save_hz", "1000"])
+  tr = IkLagrangeDualTrainer(opt)
+  assert tr.train_dataset.random_theta.is_cuda and len(tr.train_loader) == 8 and len(tr.val_loader) == 2
+  lam0 = tr.lambda_multipliers.clone()
+  w0 = [p.detach().clone() for p in tr.model.parameters()]
+  tr.main()
+  assert not torch.equal(tr.lambda_multipliers, lam0) and bool((tr.lambda_multipliers >= 0).all())
+  assert any(not torch.equal(a, b) for a, b in zip(w0, tr.model.parameters()))
+  assert all(torch.isfinite(p).all() for p in tr.model.parameters())

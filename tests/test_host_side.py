@@ -174,3 +174,38 @@ def test_single_process_dist_helpers_are_noops():
   assert D.shard_bounds(10) == (0, 10) and D.shard_bounds(10, 1, 3) == (4, 7) and D.shard_bounds(10, 2, 3) == (7, 10)
   t = torch.ones(3)
   assert D.all_reduce_sum(t) is t
+
+
+def test_device_batch_loader_covers_the_dataset_and_shards_by_rank():
+  """CPU tensors exercise the same indexing logic the GPU path uses."""
+  from ikl.configs import standard_config
+  from ikl.device_loader import DeviceBatchLoader
+  from kinematics.dataset import IkDataset
+  cfg = standard_config("cfg_joint_limits_and_4obs_dynamic")
+  n = 50
+  tensors = {"random_theta": torch.arange(n * 3, dtype=torch.float32).reshape(n, 3), "random_ee": torch.rand(n, 3),
+             "random_obstacles": torch.rand(n, 4, 4), "tensor_template": torch.cat([torch.zeros(2), torch.tensor([-2.0, 2.0]), torch.zeros(16)])}
+  ds = IkDataset.from_tensors(cfg, tensors)
+  loader = DeviceBatchLoader(ds, 16, shuffle=True, rank=0, world=1, seed=3)
+  assert len(loader) == 4
+  seen = []
+  for b in loader:
+    assert set(b.keys()) == {"input_tensor", "joint_theta", "q_ee_desired", "dynamic_obstacles"}
+    assert b["input_tensor"].shape[1] == 20 and torch.equal(b["input_tensor"][:, :2], b["q_ee_desired"][:, :2])
+    assert torch.equal(b["input_tensor"][:, 4:], b["dynamic_obstacles"].reshape(-1, 16))
+    assert torch.equal(b["input_tensor"][:, 2:4], torch.tensor([-2.0, 2.0]).expand(len(b["joint_theta"]), 2))
+    seen.append(b["joint_theta"][:, 0] / 3)
+  assert sorted(torch.cat(seen).long().tolist()) == list(range(n))
+  # item-by-item equality with the reference-style __getitem__
+  first = next(iter(DeviceBatchLoader(ds, 8, shuffle=False, rank=0, world=1)))
+  for i in range(8):
+    item = ds[i]
+    for k in item:
+      assert torch.equal(first[k][i], item[k]), k
+  # two ranks split every global batch without overlap
+  parts = [list(DeviceBatchLoader(ds, 16, shuffle=True, rank=r, world=2, seed=5)) for r in (0, 1)]
+  for b0, b1 in zip(*parts):
+    ids = torch.cat([b0["joint_theta"][:, 0], b1["joint_theta"][:, 0]]) / 3
+    assert len(set(ids.long().tolist())) == len(ids)
+  all_ids = torch.cat([b["joint_theta"][:, 0] for p in parts for b in p]) / 3
+  assert sorted(all_ids.long().tolist()) == list(range(n))
