@@ -596,3 +596,25 @@ def test_two_links_and_non_unit_link_lengths(J, lengths, cuda_device):
   from ikl import ops
   tips = ops.fk_forward_kinematics(theta.to(dev), lengths)
   close(tips[0].cpu().numpy(), O.forward_kinematics(theta.double(), lengths)[0].numpy(), scale=sum(lengths))
+
+
+@pytest.mark.parametrize("layout", ("rows", "planes"))
+def test_huge_angles_take_the_payne_hanek_path(layout, cuda_device, monkeypatch):
+  """|phi| > 1e5 leaves the packed sincos' fast range reduction: those pairs call libdevice's sincosf.  The fp32 oracle
+  performs the same fp32 angle additions, so it is the comparison (an fp64 evaluation would see different angles)."""
+  from ikl import synthetic
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  B = 2048
+  theta, q_des, obst = synthetic.make_batch(B, seed=77)
+  huge = torch.tensor([[3.0e5, -1.0, 0.5], [1.0, 2.0e6, -3.0], [-4.56e7, 0.25, 0.125], [0.5, 0.25, -1.2345e5], [1e5, 1e5, 1e5]])
+  idx = torch.tensor([0, 1, 255, 700, 2047])
+  theta[idx] = huge
+  lam = np.linspace(0.5, 2.0, 16).astype(np.float32)
+  ref = O.lagrangian_with_grad(theta, q_des, torch.from_numpy(lam), ospec, obst)
+  terms = O.lagrangian(theta, q_des, torch.from_numpy(lam), ospec, obst, per_sample=True)["per_sample_terms"]
+  viol, loss, dth, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+  assert np.isfinite(dth).all()
+  assert np.all(np.abs(viol - ref["constraint_violations"].numpy()) <= RTOL * terms.abs().sum(dim=0).numpy())
+  scale = float(ref["dtheta"].abs().max())
+  got, want = dth[idx.numpy()], ref["dtheta"].numpy()[idx.numpy()]
+  assert np.abs(got - want).max() <= 2e-5 * scale, (got, want)
