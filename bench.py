@@ -38,6 +38,32 @@ CONFIG_NAME = "cfg_joint_limits_and_4obs_dynamic"
 GOOD_SLOPE, BAD_SLOPE = 0.005, 1.0   # scripts/experiments/ik_threelink_obs4_dyn.sh:15-16
 
 
+def bind_to_gpu_numa_node(index):
+  """Run this process (and therefore its pinned host buffers, by first touch) on the CPU socket the GPU hangs off:
+  host->device copies from the far socket cross the inter-socket link and stop scaling beyond a few GPUs."""
+  try:
+    out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                         capture_output=True, text=True, timeout=20).stdout.strip()
+    bus = out.lower()
+    if bus.startswith("00000000:"):
+      bus = bus[4:]
+    node_file = "/sys/bus/pci/devices/%s/numa_node" % bus
+    node = int(open(node_file).read().strip())
+    if node < 0:
+      return None
+    cpus = []
+    for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+      lo, _, hi = part.partition("-")
+      cpus.extend(range(int(lo), int(hi or lo) + 1))
+    allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+    if allowed:
+      os.sched_setaffinity(0, allowed)
+      return {"numa_node": node, "cpus": len(allowed)}
+  except Exception:
+    return None
+  return None
+
+
 def measured_peak():
   path = os.path.join(ROOT, "MEASURED_PEAKS.json")
   try:
@@ -287,6 +313,7 @@ def run_ours(args):
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   if not torch.cuda.is_available():
     raise RuntimeError("bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback")
+  numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else None
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
@@ -476,7 +503,8 @@ def run_ours(args):
     dt = float(tt.item())
     e2e = {"value": world * Be / dt, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
            "ms_per_step": dt * 1e3, "batch_per_gpu": Be, "steps": n_e,
-           "api": "ikl.host_pipeline.HostLagrangianPipeline.run (pinned host rows-layout tensors in, host dtheta + sums out)"}
+           "api": "ikl.host_pipeline.HostLagrangianPipeline.run (pinned host rows-layout tensors in, host dtheta + sums out)",
+           "numa_bind": numa}
 
   train = None
   if not args.skip_train_step:
@@ -519,6 +547,7 @@ def main():
   ap.add_argument("--train-batch-log2", type=int, default=20)
   ap.add_argument("--skip-train-step", action="store_true")
   ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1 only: SMs left out of the persistent grid for the concurrent NCCL kernel")
+  ap.add_argument("--no-numa-bind", action="store_true")
   ap.add_argument("--skip-context", action="store_true")
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
