@@ -71,6 +71,41 @@ def measure(args):
                           "frac_of_hbm_peak": round(nbytes * B / best / 1e6 / peak, 4)}), flush=True)
 
 
+def measure_elementwise(args):
+  """The function-level drop-in kernels (level (i)): pure streaming maps, timed the same way."""
+  import torch
+  from ikl import ops, synthetic, _cabi
+  B = 1 << args.batch_log2
+  theta, q_des, obst = synthetic.make_batch(B, seed=0, device="cuda:0")
+  peak = 6548.8
+  try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+  except Exception:
+    pass
+  lim = torch.tensor([-2.094395, 2.094395], device="cuda:0").unsqueeze(0).expand(B, -1)
+  cases = [
+      ("fk_forward (12 B in, 36 B out per sample)", 48, lambda: ops.fk_forward_kinematics(theta)),
+      ("circle_penalty on column views (16 B in effective sectors ~ 5 x 4 B, 4 B out)", 24,
+       lambda: ops.circle_penalty(q_des[:, 0], q_des[:, 1], obst[:, 0, 0], obst[:, 0, 1], obst[:, 0, 2], 1.0, 0.005)),
+      ("joint_limit_penalty on a column view (4 B in, 4 B out)", 8, lambda: ops.joint_limit_penalty(theta[:, 1], lim[:, 0], lim[:, 1], 0.005, 1.0)),
+  ]
+  for name, nbytes, fn in cases:
+    for _ in range(3):
+      fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.iters):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "kernel": name, "ms_mean": round(ms, 4),
+                      "gsamples_per_s": round(B / ms / 1e6, 2), "algo_GBps": round(nbytes * B / ms / 1e6, 1),
+                      "frac_of_hbm_peak": round(nbytes * B / ms / 1e6 / peak, 4),
+                      "note": "includes the torch allocation of the output; strided column views read whole sectors"}), flush=True)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--batch-log2", type=int, default=24)
@@ -81,6 +116,8 @@ def main():
   args = ap.parse_args()
   if args.child or not args.libs:
     measure(args)
+    if not args.quick:
+      measure_elementwise(args)
     return
   for lib in args.libs.split(","):
     env = dict(os.environ, IKL_LIB=os.path.join(PKG, "lib", lib) if not os.path.isabs(lib) else lib)
