@@ -1,13 +1,11 @@
-"""Link lengths of the planar arms (reference: utils/constants.py:1-13 -- every link is 1.0 long)."""
+"""Link lengths of the planar arms, under the attribute names the reference's code reads
+(reference: utils/constants.py -- every link of every arm is one unit long)."""
+
+UNIT_LINK = 1.0
 
 
 class Constants:
-  # two-link arm
-  R2_LENGTH1 = 1.0
-  R2_LENGTH2 = 1.0
-  # three-link arm
-  R3_LENGTH1 = 1.0
-  R3_LENGTH2 = 1.0
-  R3_LENGTH3 = 1.0
-  # eight-link arm (never runnable in the reference)
-  R8_LENGTH = 1.0
+  """Manipulator geometry."""
+  R2_LENGTH1 = R2_LENGTH2 = UNIT_LINK                    # two-link arm
+  R3_LENGTH1 = R3_LENGTH2 = R3_LENGTH3 = UNIT_LINK       # three-link arm
+  R8_LENGTH = UNIT_LINK                                  # eight-link arm (its FK never ran in the reference)
