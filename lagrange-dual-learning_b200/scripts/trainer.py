@@ -259,6 +259,10 @@ class IkLagrangeDualTrainer(object):
   # ---------------------------------------------------------------------------------------------------------------
   def train_with_relaxation(self, lamda):
     """One epoch of Adam steps on the Lagrangian relaxation with the multipliers held fixed (trainer.py:251-265)."""
+    sampler = getattr(self.train_loader, "sampler", None)
+    if hasattr(sampler, "set_epoch"):           # DistributedSampler: a new permutation every relaxation epoch
+      self._relaxation_epoch = getattr(self, "_relaxation_epoch", -1) + 1
+      sampler.set_epoch(self._relaxation_epoch)
     if self.use_graph and self._graph_step is None:
       from ikl.graph_step import GraphedTrainStep
       self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size, self.device)
