@@ -121,6 +121,13 @@ IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* i
                                           void* workspace, float* viol_out, float* loss_out, double* viol_accum,
                                           float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj, void* stream);
 
+/* Backward alone: d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights w (for autograd:
+ * w_i = grad(lagrange_loss) * lambda_i + grad(constraint_violations)_i).  Recomputes from the inputs -- nothing is
+ * saved by the forward pass -- and replaces the autograd tape between lagrange_loss and the network output
+ * (scripts/trainer.py:264).  Same kernel as ikl_lagrangian_forward_backward; the sums it produces are discarded. */
+IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
+                                  float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj, void* stream);
+
 /* lambda <- max(0, lambda + multiplier_lr * viol_sum)   (scripts/trainer.py:280-284, update_multipliers).
  * viol_sum is the double running sum filled through viol_accum (or NULL to use viol_sum_f32).
  * lam_out may alias lam_in. */

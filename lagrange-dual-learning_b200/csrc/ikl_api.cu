@@ -230,6 +230,14 @@ IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* i
   return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream);
 }
 
+IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* dtheta,
+                                  int64_t dtheta_sb, int64_t dtheta_sj, void* stream) {
+  if (!workspace) return IKL_ERR_INVALID_ARGUMENT;
+  // the sums are a by-product of the pass; they land in the scratch tail of the workspace (after the completion counter)
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kPartialsBytes + 64);
+  return run(spec, in, w, workspace, scratch, scratch + kMaxK, nullptr, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream);
+}
+
 int32_t ikl_abi_version(void) { return IKL_ABI_VERSION; }
 
 void ikl_set_reserved_sms(int32_t n) { g_reserved_sms.store(n < 0 ? 0 : n, std::memory_order_relaxed); }

@@ -50,6 +50,8 @@ _SIGNATURES = {
                                               _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "ikl_lagrangian_forward_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
                                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
+    "ikl_lagrangian_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
+                                               _c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "ikl_dual_update": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_i32, _c_vp, _c_vp]),
     "ikl_fk_forward": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i32, ctypes.POINTER(_c_f), _c_vp, _c_vp]),
     "ikl_fk_backward": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i32, ctypes.POINTER(_c_f), _c_vp, _c_vp, _c_vp]),

@@ -161,6 +161,26 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
   return out[:K], out[K], dtheta
 
 
+def lagrangian_backward(spec, theta, q_ee_desired, obstacles, weights, dtheta=None):
+  """d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights (host list or CUDA tensor): the backward pass alone."""
+  lib = _cabi.load()
+  K = spec.num_constraints
+  desc, keep = _batch_desc(spec, theta, q_ee_desired, obstacles)
+  dev = theta.device
+  w = _Weights(weights, K, dev)
+  with torch.cuda.device(dev):
+    if dtheta is None:
+      if theta.dim() == 2 and theta.shape[0] > 1 and theta.stride(0) == 1:
+        dtheta = torch.empty(theta.shape[1], theta.shape[0], dtype=torch.float32, device=dev).t()
+      else:
+        dtheta = torch.empty(theta.shape, dtype=torch.float32, device=dev)
+    st = lib.ikl_lagrangian_backward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                     ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(dtheta.data_ptr()),
+                                     dtheta.stride(0), dtheta.stride(1), _stream_ptr(dev))
+  _cabi.check(st, "ikl_lagrangian_backward")
+  return dtheta
+
+
 def dual_update(lam, viol_sum, multiplier_lr, out=None):
   """lambda <- clamp(lambda + multiplier_lr * viol_sum, min=0)   (scripts/trainer.py:280-284).
 
@@ -218,7 +238,7 @@ class FusedIkLagrangian(torch.autograd.Function):
       return dtheta * grad_loss, None, None, None, None, None
     lam_dev = lam if (isinstance(lam, torch.Tensor) and lam.is_cuda) else torch.as_tensor(lam, dtype=torch.float32, device=theta.device)
     w = grad_viol if grad_loss is None else grad_viol + grad_loss * lam_dev
-    _, _, g = lagrangian_forward_backward(ctx.spec, theta.detach(), q_ee_desired, obstacles, w.contiguous())
+    g = lagrangian_backward(ctx.spec, theta.detach(), q_ee_desired, obstacles, w.contiguous())
     return g, None, None, None, None, None
 
 
