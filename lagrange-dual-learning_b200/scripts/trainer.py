@@ -169,8 +169,8 @@ class IkLagrangeDualTrainer(object):
 
     if getattr(self.opt, "device_data", False):
       from ikl.device_loader import DeviceBatchLoader
-      self.train_loader = DeviceBatchLoader(self.train_dataset, self.opt.batch_size, True, device=self.device, seed=11)
-      self.val_loader = DeviceBatchLoader(self.val_dataset, self.opt.batch_size, True, device=self.device, seed=12)
+      self.train_loader = DeviceBatchLoader(self.train_dataset, self.opt.batch_size, True, device=self.device, seed=11, planes=True)
+      self.val_loader = DeviceBatchLoader(self.val_dataset, self.opt.batch_size, True, device=self.device, seed=12, planes=True)
     else:
       self.train_loader = ikl_dist.make_loader(self.train_dataset, self.opt.batch_size, self.opt.num_workers)
       self.val_loader = ikl_dist.make_loader(self.val_dataset, self.opt.batch_size, self.opt.num_workers)
@@ -189,7 +189,10 @@ class IkLagrangeDualTrainer(object):
       return self.process_batch_unfused(inputs, lamda)
     for key in inputs:
       inputs[key] = inputs[key].to(self.device, non_blocking=True)
-    pred_joint_theta = self.model(inputs["input_tensor"])
+    # device-resident data arrives as planes: evaluate the last layer transposed so theta is planes too and the
+    # bulk-async kernel applies; otherwise the reference's row-major tensors go through the rows kernel
+    planes_in = inputs["q_ee_desired"].dim() == 2 and inputs["q_ee_desired"].shape[0] > 1 and inputs["q_ee_desired"].stride(0) == 1
+    pred_joint_theta = self.model.forward_planes(inputs["input_tensor"]) if planes_in else self.model(inputs["input_tensor"])
     q_ee_desired = inputs["q_ee_desired"]
     obstacles = inputs["dynamic_obstacles"] if self.spec.dynamic else None
     if self.spec.dynamic:
@@ -294,7 +297,9 @@ class IkLagrangeDualTrainer(object):
         for inputs in self.val_loader:
           for key in inputs:
             inputs[key] = inputs[key].to(self.device, non_blocking=True)
-          theta = self.model(inputs["input_tensor"])        # train mode (dropout on), as in the reference
+          planes_in = inputs["q_ee_desired"].shape[0] > 1 and inputs["q_ee_desired"].stride(0) == 1
+          # train mode (dropout on), as in the reference
+          theta = self.model.forward_planes(inputs["input_tensor"]) if planes_in else self.model(inputs["input_tensor"])
           fused.lagrangian_forward(self.spec, theta, inputs["q_ee_desired"],
                                    inputs["dynamic_obstacles"] if self.spec.dynamic else None, host_lam, viol_accum=total)
       ikl_dist.all_reduce_sum(total)

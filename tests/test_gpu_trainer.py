@@ -309,6 +309,30 @@ def test_trainer_with_device_resident_data(tmp_path, cuda_device):
                          "--model_save_hz", "1000"])
   tr = IkLagrangeDualTrainer(opt)
   assert tr.train_dataset.random_theta.is_cuda and len(tr.train_loader) == 8 and len(tr.val_loader) == 2
+  # the device-resident path is planes end to end: the bulk-async kernel runs inside the real trainer step, and it
+  # computes the same loss and weight gradients as the row-major path on the same batch
+  from ikl import _cabi
+  tr.model.eval()
+  batch = next(iter(tr.train_loader))
+  assert batch["q_ee_desired"].stride(0) == 1 and batch["dynamic_obstacles"].stride(0) == 1
+  out_p = tr.process_batch(dict(batch), tr.lambda_multipliers)
+  assert "planes_tma" in _cabi.last_kernel_name() and out_p["pred_joint_theta"].stride(0) == 1
+  tr.model.zero_grad()
+  out_p["lagrange_loss"].backward()
+  g_p = [p.grad.clone() for p in tr.model.parameters()]
+  rows = {"input_tensor": batch["input_tensor"], "q_ee_desired": batch["q_ee_desired"].contiguous(),
+          "dynamic_obstacles": torch.cat([batch["dynamic_obstacles"], torch.zeros(8192, 4, 1, device=tr.device)], dim=2).contiguous()}
+  out_r = tr.process_batch(rows, tr.lambda_multipliers)
+  assert "<rows," in _cabi.last_kernel_name()
+  tr.model.zero_grad()
+  out_r["lagrange_loss"].backward()
+  lp, lr = float(out_p["lagrange_loss"].detach()), float(out_r["lagrange_loss"].detach())
+  assert abs(lp - lr) <= 1e-5 * abs(lr)
+  for a, p in zip(g_p, tr.model.parameters()):
+    assert float((a - p.grad).abs().max()) <= 2e-5 * max(float(p.grad.abs().max()), 1e-6)
+  assert torch.equal(out_p["q_ee_actual"], out_r["q_ee_actual"])
+  tr.model.train()
+  tr.model.zero_grad()
   lam0 = tr.lambda_multipliers.clone()
   w0 = [p.detach().clone() for p in tr.model.parameters()]
   tr.main()
