@@ -6,6 +6,8 @@
 
 #include <atomic>
 
+#include <cuda.h>          // CUtensorMap types only; the encoder is looked up at run time (no link against libcuda)
+
 #include "ikl_lagrangian.cuh"
 
 namespace ikl {
@@ -119,6 +121,45 @@ void fill_packed_uniforms(const IklSpec* spec, const Uniforms& u, PackedUniforms
   for (int i = 0; i < kMaxK; ++i) pu.lam[i] = dup(u.w[i]);
 }
 
+
+// ---- TMA descriptors ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled lives in the driver; libikl.so links cudart statically and asks it for the entry point.
+#ifndef IKL_TMA_L2_PROMOTION
+#define IKL_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// A group of `n1 x n2` fp32 planes of `batch` samples each as a rank-2 (n2 == 0) or rank-3 tensor, sample index innermost;
+// box = 256 samples x the whole group.  Strides are in elements.  Returns false when the hardware cannot describe it.
+bool encode_planes(TensorMap* out, const float* base, int64_t batch, int n1, int64_t stride1, int n2, int64_t stride2) {
+  static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) >= alignof(CUtensorMap), "TensorMap must mirror CUtensorMap");
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  if (stride1 <= 0 || (stride1 * 4) % 16 != 0 || (n2 > 0 && (stride2 <= 0 || (stride2 * 4) % 16 != 0))) return false;
+  const cuuint32_t rank = n2 > 0 ? 3 : 2;
+  const cuuint64_t dims[3] = {(cuuint64_t)batch, (cuuint64_t)n1, (cuuint64_t)(n2 > 0 ? n2 : 1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)stride1 * 4, (cuuint64_t)stride2 * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kTmaBox, (cuuint32_t)n1, (cuuint32_t)(n2 > 0 ? n2 : 1)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, IKL_TMA_L2_PROMOTION,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 bool unit_links(const IklSpec* spec) {
   for (int m = 0; m < spec->num_links; ++m)
     if (spec->link_length[m] != 1.0f) return false;
@@ -180,9 +221,14 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
     const bool dyn = v.dyn;
     const char* e = getenv("IKL_PLANES_TMA");
     const bool want = !(e && e[0] == '0');
-    p.use_tma = want && in->batch % 4 == 0 && in->batch >= 4 && aligned16(in->theta) && in->theta_sj % 4 == 0 && aligned16(in->target) &&
-                in->target_sc % 4 == 0 &&
+    p.use_tma = want && in->batch % 4 == 0 && in->batch >= 4 && in->batch < (int64_t(1) << 31) - 2 * kTmaTile && aligned16(in->theta) &&
+                in->theta_sj % 4 == 0 && aligned16(in->target) && in->target_sc % 4 == 0 &&
                 (!dyn || (aligned16(in->obstacles) && in->obst_so % 4 == 0 && in->obst_sc % 4 == 0));
+    if (p.use_tma) {
+      p.use_tma = encode_planes(&p.tm_theta, in->theta, in->batch, 3, in->theta_sj, 0, 0) &&
+                  encode_planes(&p.tm_target, in->target, in->batch, 2, in->target_sc, 0, 0) &&
+                  (!dyn || encode_planes(&p.tm_obst, in->obstacles, in->batch, 3, in->obst_sc, v.nobs, in->obst_so));
+    }
   }
   const int forced = forced_layout();
   if (forced == kStrided) layout = kStrided;                 // the generic kernel accepts anything

@@ -27,7 +27,10 @@ namespace ikl {
 #endif
 constexpr int kThreads = IKL_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kFlushSamples = 64;   // samples a thread adds in fp32 before flushing into its fp64 slot in shared memory
+#ifndef IKL_FLUSH_SAMPLES
+#define IKL_FLUSH_SAMPLES 64
+#endif
+constexpr int kFlushSamples = IKL_FLUSH_SAMPLES;   // samples a thread adds in fp32 before flushing into its fp64 slot in shared memory
 constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last-block reduce
 
 #ifndef IKL_ROWS_UNROLL
@@ -39,6 +42,8 @@ constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last
 
 enum Layout : int { kStrided = 0, kRows = 1, kPlanes = 2 };
 enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
+
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };      // same size and alignment as the driver's CUtensorMap
 
 struct LagrangianParams {
   Uniforms u;
@@ -56,8 +61,12 @@ struct LagrangianParams {
   float* viol_out;
   float* loss_out;
   double* viol_accum;   // or null
-  int use_tma;          // planes layout: bulk-async staged kernel (needs batch % 4 == 0 and 16-byte aligned planes)
+  int use_tma;          // planes layout: TMA-staged kernel (needs batch % 4 == 0, 16-byte aligned planes, plane strides % 4 == 0)
+  // TMA descriptors of the planes as 2-D / 3-D tensors (sample index innermost), encoded by the host per call:
+  // theta {B, 3}, target {B, 2}, obstacles {B, 3, n}; box = 256 samples x every plane of the group.
+  TensorMap tm_theta, tm_target, tm_obst;
 };
+static_assert(sizeof(LagrangianParams) <= 4096, "kernel parameter block too large");
 
 template <int LAYOUT_, int J_, int NOBS_, bool DYN_, bool JL_, int MODE_, bool UNIT_>
 struct Cfg {
@@ -195,6 +204,45 @@ struct WarpAcc {
       acc[i] = f2_splat(0.f);
     }
     if (++n1 == 64) deep_flush();
+  }
+};
+
+// Warp-level second level for the barrier-free bulk-async gradient kernel: every kFlushSamples samples per thread the
+// K packed fp32 running sums of a warp are reduced across its lanes with a transposing butterfly (16 + 8 + 4 + 2 + 1
+// shuffles instead of 5 per constraint) and lane i adds constraint i's warp total to one fp64 slot in shared memory.
+// 1 KiB of shared memory per block instead of SharedAcc's 32 KiB -- which buys the third staging buffer.
+template <int K>
+struct WarpSharedAcc {
+  double (*s_warp)[kMaxK];
+  __device__ __forceinline__ explicit WarpSharedAcc(double (*sw)[kMaxK]) : s_warp(sw) {
+    if (threadIdx.x < kWarps * kMaxK) (&sw[0][0])[threadIdx.x] = 0.0;
+  }
+  static constexpr int N = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : 16;      // vector length: next power of two >= K
+  __device__ __forceinline__ void flush(f2 (&acc)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = i < K ? f2_lo(acc[i]) + f2_hi(acc[i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = f2_splat(0.f);
+    // transposing steps: a lane keeps the half of the vector selected by its `off` bit and adds its partner's copy of it
+    int idx = 0, off = 16;
+#pragma unroll
+    for (int n = N / 2; n >= 1; n >>= 1, off >>= 1) {
+      const bool up = (lane & off) != 0;
+      idx += up ? n : 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const float keep = up ? v[i + n] : v[i];
+        const float send = up ? v[i] : v[i + n];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    // plain butterfly over the remaining lane bits
+    const int rest = 2 * off - 1;            // mask of the lane bits not used for transposing
+#pragma unroll
+    for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    if ((lane & rest) == 0 && idx < K) s_warp[warp][idx] += (double)v[0];
   }
 };
 
@@ -480,17 +528,39 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "r"(bytes), "r"(bar) : "memory");
 }
 
-// Measured on B200 (profiles/r01/kernel_table_v3_tma*.jsonl): the gradient kernel is register-bound, so it keeps its
-// fp64 second-level sums in shared memory (SharedAcc) and stages two tiles; the forward kernel has registers to spare,
-// keeps them in registers (WarpAcc) and spends the shared memory on a third stage.
+// Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
+// are zero-filled by the hardware, so ragged last tiles need no special case.
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const TensorMap* tm, int x, int y, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tm), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const TensorMap* tm, int x, int y, int z, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+constexpr int kTmaBox = 256;                           // samples per TMA box (the hardware limit per box dimension)
+constexpr int kTmaBoxBytes = kTmaBox * 4;
+
+// Shared-memory budget of the staged kernels.  IKL_TMA_PIPE = 0: the round-1 form (block barrier per tile; the gradient
+// kernel keeps per-thread fp64 sums in shared memory and stages two tiles, the forward kernel keeps them in registers and
+// stages three).  IKL_TMA_PIPE = 1: barrier-free pipeline (run_planes_pipe): warp-level sums (1 KiB), IKL_TMA_STAGES tiles.
+#ifndef IKL_TMA_PIPE
+#define IKL_TMA_PIPE 1
+#endif
+#ifndef IKL_TMA_STAGES
+#define IKL_TMA_STAGES 2
+#endif
+#ifndef IKL_PIPE_PROXY_FENCE
+#define IKL_PIPE_PROXY_FENCE 1
+#endif
 template <class C>
 struct TmaLayout {
   static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
   static constexpr int kStageBytes = kPlanes * kTmaPlaneBytes;
-  static constexpr bool kSharedAcc = C::GRAD;
-  static constexpr int kStages = C::GRAD ? 2 : 3;
+  static constexpr bool kSharedAcc = IKL_TMA_PIPE ? false : C::GRAD;
+  static constexpr int kStages = IKL_TMA_PIPE ? IKL_TMA_STAGES : (C::GRAD ? 2 : 3);
   static constexpr size_t kAccBytes = kSharedAcc ? sizeof(SharedAcc<C::K>) : 0;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAccBytes + 64;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAccBytes + 128;
 };
 
 template <class C, class W2, class Acc>
@@ -584,6 +654,124 @@ __device__ __forceinline__ void run_planes_tma(const LagrangianParams& p, const 
   sacc.flush(acc);
 }
 
+// Barrier-free form of the staged kernel.  A thread reads its 17 operands from a stage at the START of a tile and then
+// computes for ~450 instructions without touching shared memory, so the stage can be handed back as soon as every warp
+// has done its loads -- not a whole tile later, and without a block barrier.  Each warp arrives on the stage's "drained" mbarrier
+// (count = warps per block) after its loads; the warp whose arrival completes the phase re-arms the stage's "full" mbarrier
+// and issues the bulk copies of the tile that goes there next.  Nobody waits for anybody except for data.
+// Arrive on an mbarrier (release: the caller's shared-memory reads are performed first) and report whether this was the
+// arrival that completed the phase: the returned state is the one BEFORE the arrival, so a pending count of 1 means "last".
+__device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
+  unsigned long long state;
+  unsigned pending;
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
+  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+  return pending == 1u;
+}
+
+template <class C, class W2, class Acc>
+__device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const W2& w2, Acc& sacc, unsigned char* stage_mem,
+                                                unsigned long long* bars) {
+  using L = TmaLayout<C>;
+  constexpr int S = L::kStages;
+  const long long B = p.batch;
+  const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
+  const unsigned drained0 = bar0 + 8 * S;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(drained0 + 8 * s, kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Stage layout: [half (2)][plane][256 samples]; each half is what one box of every group delivers.
+  auto issue = [&](long long tile, int stage) {      // one thread
+    const int b0 = (int)(tile * kTmaTile);
+    const unsigned bar = bar0 + 8 * stage;
+    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
+    mbar_expect_tx(bar, (unsigned)L::kStageBytes);    // boxes always deliver their full size (zero-filled past the batch end)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned d = dst + h * (L::kPlanes * kTmaBoxBytes);
+      const int x = b0 + h * kTmaBox;
+      tma_load_2d(d, &p.tm_theta, x, 0, bar);
+      tma_load_2d(d + 3 * kTmaBoxBytes, &p.tm_target, x, 0, bar);
+      if (C::DYN) tma_load_3d(d + 5 * kTmaBoxBytes, &p.tm_obst, x, 0, 0, bar);
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+
+  f2 acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  int since_flush = 0, stage = 0;
+  unsigned parity = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar0 + 8 * stage, parity);
+    const long long b = tile * kTmaTile + 2 * tid;
+    const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * (L::kPlanes * kTmaBoxBytes) + 8 * (tid & 127);
+    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    int pl = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
+    const f2 tx = *reinterpret_cast<const f2*>(base + 3 * kTmaBoxBytes);
+    const f2 ty = *reinterpret_cast<const f2*>(base + 4 * kTmaBoxBytes);
+    pl = 5;
+    if (C::DYN) {
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c, ++pl) ob[k][c] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
+      }
+    } else {
+      static_obstacles_packed<C>(p, ob);
+    }
+    // hand the stage back: the last of the block's warps to get here refills it
+    __syncwarp();
+    if (lane == 0) {
+      const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
+      const long long next = tile + (long long)S * gridDim.x;
+      if (last && next < ntiles) {
+#if IKL_PIPE_PROXY_FENCE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        issue(next, stage);
+      }
+    }
+    __syncwarp();
+    if (b < B) {
+      eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+      if (C::GRAD) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
+      } else {
+        store_side_outputs(p, b, b + 1, ee, tx, ty);
+      }
+    }
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      sacc.flush(acc);
+    }
+    if (++stage == S) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  sacc.flush(acc);
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -599,6 +787,15 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
     }
     __syncthreads();
   }
+#if IKL_TMA_PIPE
+  {
+    WarpSharedAcc<C::K> sacc(s_warp);
+    auto run_pipe = [&](const auto& w2) { run_planes_pipe<C>(p, w2, sacc, stage_mem, bars); };
+    if constexpr (C::MODE == kGradDevW) run_pipe(PackedSmemWeights{s_lam2});
+    else run_pipe(PackedHostWeights{p.pu});
+    block_finalize<C::K>(p, s_warp);
+  }
+#else
   auto run = [&](auto& sacc) {
     if constexpr (C::MODE == kGradDevW) {
       const PackedSmemWeights w2{s_lam2};
@@ -620,6 +817,7 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
     sacc.deep_flush();
     block_finalize<C::K>(p, s_warp);
   }
+#endif
 }
 
 template <class C>
