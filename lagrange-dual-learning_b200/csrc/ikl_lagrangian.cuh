@@ -172,45 +172,10 @@ __device__ __forceinline__ void finalize_sums(const LagrangianParams& p, SharedA
   block_finalize<K>(p, s_red);
 }
 
-// Register-resident second level for the bulk-async kernel (its shared memory goes to the staging buffers):
-// level 0 = packed fp32 running sums (<= 64 samples), level 1 = K fp32 registers (<= 64 level-0 flushes), level 2 =
-// one fp64 slot per (warp, constraint) in shared memory, reached through a warp-shuffle reduction every 4096 samples.
-template <int K>
-struct WarpAcc {
-  double (*s_warp)[kMaxK];
-  float acc1[K];
-  int n1;
-  __device__ __forceinline__ explicit WarpAcc(double (*sw)[kMaxK]) : s_warp(sw), n1(0) {
-#pragma unroll
-    for (int i = 0; i < K; ++i) acc1[i] = 0.f;
-    if (threadIdx.x < kWarps * kMaxK) (&sw[0][0])[threadIdx.x] = 0.0;
-  }
-  __device__ __forceinline__ void deep_flush() {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      double v = (double)acc1[i];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0) s_warp[warp][i] += v;
-      acc1[i] = 0.f;
-    }
-    n1 = 0;
-  }
-  __device__ __forceinline__ void flush(f2 (&acc)[K]) {
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      acc1[i] += f2_lo(acc[i]) + f2_hi(acc[i]);
-      acc[i] = f2_splat(0.f);
-    }
-    if (++n1 == 64) deep_flush();
-  }
-};
-
-// Warp-level second level for the barrier-free bulk-async gradient kernel: every kFlushSamples samples per thread the
+// Warp-level second level for the TMA-staged kernels: every kFlushSamples samples per thread the
 // K packed fp32 running sums of a warp are reduced across its lanes with a transposing butterfly (16 + 8 + 4 + 2 + 1
 // shuffles instead of 5 per constraint) and lane i adds constraint i's warp total to one fp64 slot in shared memory.
-// 1 KiB of shared memory per block instead of SharedAcc's 32 KiB -- which buys the third staging buffer.
+// 1 KiB of shared memory per block instead of SharedAcc's 32 KiB, and no extra registers in the hot loop.
 template <int K>
 struct WarpSharedAcc {
   double (*s_warp)[kMaxK];
@@ -495,15 +460,12 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
   sacc.flush(sacc1);
 }
 
-// ---- planes layout, bulk-async staged (TMA 1-D copies + mbarrier) -------------------------------------------------
-// Each 512-sample tile of every plane is a contiguous 2 KiB run in HBM.  One elected thread issues one
-// cp.async.bulk (SASS UBLKCP) per plane into a shared-memory stage and arms the stage's mbarrier with the byte count;
-// the 256 compute threads wait on the barrier, read their pair of samples with LDS.64 at immediate offsets (no
-// per-plane address arithmetic, no long-scoreboard stalls) and write d/dtheta straight to HBM.  Two stages: tile k+1
-// is in flight while tile k is evaluated.
+// ---- planes layout, TMA-staged ---------------------------------------------------------------------------------------
+// The planes of a batch are three tensors with the sample index innermost: theta {B, 3}, target {B, 2}, obstacles
+// {B, 3, n}.  A 512-sample tile is two 256-sample boxes (the hardware limit per box dimension) of each tensor: six tiled
+// TMA loads (SASS UTMALDG) land a whole tile of all 17 planes in one shared-memory stage and complete on the stage's
+// mbarrier.  Threads read their pair of samples with LDS.64 at immediate offsets and write d/dtheta straight to HBM.
 constexpr int kTmaTile = 2 * kThreads;                 // samples per tile
-
-constexpr int kTmaPlaneBytes = kTmaTile * 4;           // 2048
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -523,11 +485,6 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "IKL_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar) : "memory");
-}
-
 // Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
 // are zero-filled by the hardware, so ragged last tiles need no special case.
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const TensorMap* tm, int x, int y, unsigned bar) {
@@ -541,12 +498,8 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const TensorMap* tm, i
 constexpr int kTmaBox = 256;                           // samples per TMA box (the hardware limit per box dimension)
 constexpr int kTmaBoxBytes = kTmaBox * 4;
 
-// Shared-memory budget of the staged kernels.  IKL_TMA_PIPE = 0: the round-1 form (block barrier per tile; the gradient
-// kernel keeps per-thread fp64 sums in shared memory and stages two tiles, the forward kernel keeps them in registers and
-// stages three).  IKL_TMA_PIPE = 1: barrier-free pipeline (run_planes_pipe): warp-level sums (1 KiB), IKL_TMA_STAGES tiles.
-#ifndef IKL_TMA_PIPE
-#define IKL_TMA_PIPE 1
-#endif
+// Shared-memory budget: IKL_TMA_STAGES stages of [half (2)][plane][256 samples] + the mbarriers.  Measured on B200
+// (profiles/r01/kernel_table_pipeline.jsonl): 2 stages 0.2166 ms, 3 stages 0.2200 ms, 1 stage 0.2199 ms (fwd+bwd, 2^24).
 #ifndef IKL_TMA_STAGES
 #define IKL_TMA_STAGES 2
 #endif
@@ -556,109 +509,12 @@ constexpr int kTmaBoxBytes = kTmaBox * 4;
 template <class C>
 struct TmaLayout {
   static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
-  static constexpr int kStageBytes = kPlanes * kTmaPlaneBytes;
-  static constexpr bool kSharedAcc = IKL_TMA_PIPE ? false : C::GRAD;
-  static constexpr int kStages = IKL_TMA_PIPE ? IKL_TMA_STAGES : (C::GRAD ? 2 : 3);
-  static constexpr size_t kAccBytes = kSharedAcc ? sizeof(SharedAcc<C::K>) : 0;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAccBytes + 128;
+  static constexpr int kHalfBytes = kPlanes * kTmaBoxBytes;
+  static constexpr int kStageBytes = 2 * kHalfBytes;
+  static constexpr int kStages = IKL_TMA_STAGES;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
 };
 
-template <class C, class W2, class Acc>
-__device__ __forceinline__ void run_planes_tma(const LagrangianParams& p, const W2& w2, Acc& sacc, unsigned char* stage_mem,
-                                               unsigned long long* bars) {
-  using L = TmaLayout<C>;
-  constexpr int kTmaStages = L::kStages;
-  const long long B = p.batch;
-  const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
-  const int tid = threadIdx.x;
-  const unsigned bar0 = smem_u32(bars);
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(bar0 + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  auto issue = [&](long long tile, int stage) {      // thread 0 only
-    const long long b0 = tile * kTmaTile;
-    const long long left = B - b0;
-    const unsigned bytes = (unsigned)((left < kTmaTile ? left : kTmaTile) * 4);   // multiple of 16: the API requires B % 4 == 0
-    const unsigned bar = bar0 + 8 * stage;
-    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
-    mbar_expect_tx(bar, bytes * L::kPlanes);
-    int pl = 0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.theta + j * p.th_sj + b0, bytes, bar);
-#pragma unroll
-    for (int c = 0; c < 2; ++c, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.target + c * p.tg_sc + b0, bytes, bar);
-    if (C::DYN) {
-#pragma unroll
-      for (int k = 0; k < C::NOBS; ++k) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c, ++pl) bulk_g2s(dst + pl * kTmaPlaneBytes, p.obst + k * p.ob_so + c * p.ob_sc + b0, bytes, bar);
-      }
-    }
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (t < ntiles) issue(t, s);
-    }
-  }
-
-  f2 acc[C::K];
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  int since_flush = 0, it = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it % kTmaStages;
-    const unsigned parity = (unsigned)(it / kTmaStages) & 1u;
-    mbar_wait(bar0 + 8 * stage, parity);
-    const long long b = tile * kTmaTile + 2 * tid;
-    if (b < B) {
-      const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + 8 * tid;
-      f2 th[3], ob[C::NOB][3], dth[3], ee[3];
-      int pl = 0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaPlaneBytes);
-      const f2 tx = *reinterpret_cast<const f2*>(base + 3 * kTmaPlaneBytes);
-      const f2 ty = *reinterpret_cast<const f2*>(base + 4 * kTmaPlaneBytes);
-      pl = 5;
-      if (C::DYN) {
-#pragma unroll
-        for (int k = 0; k < C::NOBS; ++k) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c, ++pl) ob[k][c] = *reinterpret_cast<const f2*>(base + pl * kTmaPlaneBytes);
-        }
-      } else {
-        static_obstacles_packed<C>(p, ob);
-      }
-      eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
-      if (C::GRAD) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
-      } else {
-        store_side_outputs(p, b, b + 1, ee, tx, ty);
-      }
-    }
-    if (++since_flush == kFlushSamples / 2) {
-      since_flush = 0;
-      sacc.flush(acc);
-    }
-    __syncthreads();                                  // every thread is done reading this stage
-    const long long next = tile + (long long)kTmaStages * gridDim.x;
-    if (tid == 0 && next < ntiles) issue(next, stage);
-  }
-  sacc.flush(acc);
-}
-
-// Barrier-free form of the staged kernel.  A thread reads its 17 operands from a stage at the START of a tile and then
-// computes for ~450 instructions without touching shared memory, so the stage can be handed back as soon as every warp
-// has done its loads -- not a whole tile later, and without a block barrier.  Each warp arrives on the stage's "drained" mbarrier
-// (count = warps per block) after its loads; the warp whose arrival completes the phase re-arms the stage's "full" mbarrier
-// and issues the bulk copies of the tile that goes there next.  Nobody waits for anybody except for data.
 // Arrive on an mbarrier (release: the caller's shared-memory reads are performed first) and report whether this was the
 // arrival that completed the phase: the returned state is the one BEFORE the arrival, so a pending count of 1 means "last".
 __device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
@@ -669,11 +525,19 @@ __device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
   return pending == 1u;
 }
 
+// Barrier-free pipeline.  A thread reads its operands from a stage at the START of a tile and then computes for ~450
+// instructions without touching shared memory, so the stage is handed back as soon as every warp has done its loads --
+// not a whole tile later, and without a block barrier.  Each warp arrives on the stage's "drained" mbarrier (count =
+// warps per block) after its loads; the warp whose arrival completes the phase re-arms the stage's "full" mbarrier and
+// issues the TMA loads of the tile that goes there next.  Nobody waits for anybody, only for data.  (Round-1 history,
+// profiles/r01/README.md: with 17 one-dimensional bulk copies per tile the issuing warp ran ~45 % more instructions than
+// its siblings and throttled the block whichever warp it was; six UTMALDG make the refill cheap enough to hand around.)
 template <class C, class W2, class Acc>
 __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const W2& w2, Acc& sacc, unsigned char* stage_mem,
                                                 unsigned long long* bars) {
   using L = TmaLayout<C>;
   constexpr int S = L::kStages;
+  static_assert(kThreads == kTmaBox, "thread v of a 512-sample tile owns samples (2v, 2v+1): half = v / 128");
   const long long B = p.batch;
   const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -697,7 +561,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const
     mbar_expect_tx(bar, (unsigned)L::kStageBytes);    // boxes always deliver their full size (zero-filled past the batch end)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const unsigned d = dst + h * (L::kPlanes * kTmaBoxBytes);
+      const unsigned d = dst + h * L::kHalfBytes;
       const int x = b0 + h * kTmaBox;
       tma_load_2d(d, &p.tm_theta, x, 0, bar);
       tma_load_2d(d + 3 * kTmaBoxBytes, &p.tm_target, x, 0, bar);
@@ -721,7 +585,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar0 + 8 * stage, parity);
     const long long b = tile * kTmaTile + 2 * tid;
-    const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * (L::kPlanes * kTmaBoxBytes) + 8 * (tid & 127);
+    const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
     f2 th[3], ob[C::NOB][3], dth[3], ee[3];
     int pl = 0;
 #pragma unroll
@@ -777,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   using L = TmaLayout<C>;
   unsigned char* stage_mem = dyn_smem;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes + L::kAccBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
   __shared__ float2 s_lam2[kMaxK];
   __shared__ double s_warp[kWarps][kMaxK];
   if constexpr (C::MODE == kGradDevW) {
@@ -785,39 +649,11 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
       const float l = __ldg(p.w_dev + threadIdx.x);
       s_lam2[threadIdx.x] = make_float2(l, l);
     }
-    __syncthreads();
   }
-#if IKL_TMA_PIPE
-  {
-    WarpSharedAcc<C::K> sacc(s_warp);
-    auto run_pipe = [&](const auto& w2) { run_planes_pipe<C>(p, w2, sacc, stage_mem, bars); };
-    if constexpr (C::MODE == kGradDevW) run_pipe(PackedSmemWeights{s_lam2});
-    else run_pipe(PackedHostWeights{p.pu});
-    block_finalize<C::K>(p, s_warp);
-  }
-#else
-  auto run = [&](auto& sacc) {
-    if constexpr (C::MODE == kGradDevW) {
-      const PackedSmemWeights w2{s_lam2};
-      run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
-    } else {
-      const PackedHostWeights w2{p.pu};
-      run_planes_tma<C>(p, w2, sacc, stage_mem, bars);
-    }
-  };
-  if constexpr (L::kSharedAcc) {
-    SharedAcc<C::K>& sacc = *reinterpret_cast<SharedAcc<C::K>*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
-    sacc.clear();
-    run(sacc);
-    finalize_sums<C::K>(p, sacc);
-  } else {
-    WarpAcc<C::K> sacc(s_warp);
-    __syncthreads();                 // s_warp is zeroed by other warps' threads
-    run(sacc);
-    sacc.deep_flush();
-    block_finalize<C::K>(p, s_warp);
-  }
-#endif
+  WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
+  if constexpr (C::MODE == kGradDevW) run_planes_pipe<C>(p, PackedSmemWeights{s_lam2}, sacc, stage_mem, bars);
+  else run_planes_pipe<C>(p, PackedHostWeights{p.pu}, sacc, stage_mem, bars);
+  block_finalize<C::K>(p, s_warp);
 }
 
 template <class C>

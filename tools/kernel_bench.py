@@ -35,12 +35,16 @@ def measure(args):
            ("cfg_joint_limits", 32, 20), ("cfg_no_constraints", 32, 20)]
   if args.quick:
     cases = cases[:1]
+  if args.configs:
+    cases = [c for c in cases if any(c[0].endswith(n) for n in args.configs.split(","))]
   for cfg_name, bytes_fb, bytes_f in cases:
     spec = ConstraintSpec.from_config(standard_config(cfg_name), 3, 0.005, 1.0)
     K = spec.num_constraints
     lam = [1.0 + 0.1 * i for i in range(K)]
     lam_dev = torch.tensor(lam, device=dev)
     for lname, (th, tg, ob) in (("planes", planes), ("rows", rows)):
+      if args.layouts and lname not in args.layouts.split(","):
+        continue
       dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
       for mode in ("fwdbwd_hostw", "fwdbwd_devw", "fwd"):
         if args.quick and mode == "fwdbwd_devw":
@@ -112,11 +116,13 @@ def main():
   ap.add_argument("--iters", type=int, default=30)
   ap.add_argument("--libs", default="")
   ap.add_argument("--quick", action="store_true")
+  ap.add_argument("--configs", default="", help="comma-separated config-name suffixes to keep, e.g. 4obs_static,no_constraints")
+  ap.add_argument("--layouts", default="", help="planes and/or rows")
   ap.add_argument("--child", action="store_true")
   args = ap.parse_args()
   if args.child or not args.libs:
     measure(args)
-    if not args.quick:
+    if not args.quick and not args.configs and not args.layouts:
       measure_elementwise(args)
     return
   for lib in args.libs.split(","):
@@ -124,6 +130,10 @@ def main():
     cmd = [sys.executable, os.path.abspath(__file__), "--child", "--batch-log2", str(args.batch_log2), "--iters", str(args.iters)]
     if args.quick:
       cmd.append("--quick")
+    if args.configs:
+      cmd += ["--configs", args.configs]
+    if args.layouts:
+      cmd += ["--layouts", args.layouts]
     subprocess.run(cmd, env=env, check=False)
 
 
