@@ -334,6 +334,62 @@ def test_ragged_and_empty_batches(B, cuda_device, monkeypatch):
     grad_close(dth, dth64, truth)
 
 
+@pytest.mark.parametrize("B", [4, 8, 252, 256, 260, 508, 512, 516, 1028, 151556])
+def test_tma_pipeline_ragged_tiles_all_configs(B, cuda_device, monkeypatch):
+  """The TMA-staged planes kernel: batches smaller than a box, exactly one box / tile, tiles whose tail the hardware
+  zero-fills, and a batch that gives every block of the persistent grid one full tile and one 4-sample tile
+  (151556 = 296 * 512 + 4) -- for every task config, forward-only and fwd+bwd with host- and device-side multipliers."""
+  from ikl import synthetic
+  theta, q_des, obst = synthetic.make_batch(B, seed=1000 + B)
+  for name in CONFIG_NAMES:
+    spec, ospec = specs_for(name)
+    K = spec.num_constraints
+    lam = (0.75 + 0.125 * np.arange(K)).astype(np.float32)
+    sums64, abs_sums, dth64, kink, truth = oracle_truth(ospec, theta, q_des, obst, lam)
+    results = []
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(cuda_device)):
+      viol, loss, dth, kname = run_layout("planes", spec, theta, q_des, obst, weights, True, monkeypatch)
+      assert "<planes_tma," in kname, kname
+      assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums + 1e-30), (name, B)
+      grad_close(dth, dth64, truth)
+      results.append((viol, dth))
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][0], results[1][0])
+    viol_f, _, _, kname = run_layout("planes", spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
+    assert "<planes_tma," in kname and np.array_equal(viol_f, results[0][0])
+    # the same samples in the reference's row-major layout: identical gradient on the full 512-sample tiles
+    viol_r, _, dth_r, _ = run_layout("rows", spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    full = (B // 512) * 512
+    assert np.array_equal(dth_r[:full], results[0][1][:full])
+    assert np.all(np.abs(viol_r - results[0][0]) <= 2e-6 * abs_sums + 1e-30)
+
+
+def test_tma_pipeline_padded_and_irregular_plane_strides(cuda_device, monkeypatch):
+  """Planes that live in bigger allocations: plane stride > batch, obstacle planes whose per-obstacle stride is not three
+  per-coordinate strides (a 3-D tensor map), planes that are not in theta/target/obstacle order in memory."""
+  from ikl import fused, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  dev = cuda_device
+  B, pad = 6000, 36
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  theta, q_des, obst = synthetic.make_batch(B, seed=5)
+  lam = [0.5 + 0.1 * i for i in range(16)]
+  th0, tg0, ob0 = synthetic.to_planes(theta.to(dev), q_des.to(dev), obst.to(dev))
+  v0, l0, d0 = fused.lagrangian_forward_backward(spec, th0, tg0, ob0, lam)
+  assert "<planes_tma," in _cabi.last_kernel_name()
+  v0, d0 = v0.clone(), d0.contiguous().clone()
+  arena = torch.full((40, B + pad), float("nan"), device=dev)          # rows of the arena = candidate planes
+  ob_store = arena[8:8 + 20].view(4, 5, B + pad)                        # obstacle o: rows 8+5o .. 8+5o+2 (stride 5 planes per obstacle)
+  th_store, tg_store = arena[33:36], arena[2:4]                         # theta AFTER the obstacles, target before them
+  th_store[:, :B] = theta.t().to(dev)
+  tg_store[:, :B] = q_des[:, :2].t().to(dev)
+  ob_store[:, :3, :B] = obst[:, :, :3].permute(1, 2, 0).to(dev)
+  thp, tgp, obp = th_store[:, :B].t(), tg_store[:, :B].t(), ob_store[:, :3, :B].permute(2, 0, 1)
+  dth = torch.empty_strided((B, 3), (1, B + pad), dtype=torch.float32, device=dev)
+  v1, l1, d1 = fused.lagrangian_forward_backward(spec, thp, tgp, obp, lam, dtheta=dth)
+  assert "<planes_tma," in _cabi.last_kernel_name()
+  assert torch.equal(v1, v0) and torch.equal(d1.contiguous(), d0) and float(l1) == float(l0)
+
+
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
   """theta exactly at a limit / at mid-range, a tip exactly on a circle, a tip exactly on a centre."""
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
