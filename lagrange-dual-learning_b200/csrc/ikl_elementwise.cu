@@ -23,6 +23,13 @@ inline unsigned ew_grid(long long n) {
 
 struct Lengths { float v[IKL_MAX_LINKS]; };
 
+// Elements per thread per grid-stride step.  The penalty kernels read a few 4-byte elements per sample from strided column
+// views; with one sample per thread an SM has too few bytes in flight to cover the HBM latency (jl_forward: 41 % of the
+// measured peak on physical bytes), so every thread issues the loads of kEwUnroll samples before touching any of them.
+constexpr int kEwUnroll = 4;
+
+inline unsigned ew_grid_unrolled(long long n) { return ew_grid((n + kEwUnroll - 1) / kEwUnroll); }
+
 // kinematics/forward_kinematics.py:64-81 -- tips_out block k = tip J-k (end effector first), rows (x, y, angle)
 template <int J>
 __global__ void __launch_bounds__(kEwThreads) fk_forward_kernel(const float* __restrict__ theta, long long sb, long long sj, long long B,
@@ -76,12 +83,25 @@ __global__ void __launch_bounds__(kEwThreads) circle_forward_kernel(const float*
                                                                    const float* __restrict__ oy, long long s_oy,
                                                                    const float* __restrict__ rad, long long s_r, long long n, float a_in,
                                                                    float a_out, float* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kEwThreads) {
-    const float dx = __fsub_rn(jx[i * s_jx], ox[i * s_ox]);
-    const float dy = __fsub_rn(jy[i * s_jy], oy[i * s_oy]);
-    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    const float t = __fsub_rn(d, rad[i * s_r]);
-    out[i] = torch_max(__fmul_rn(-a_in, t), __fmul_rn(-a_out, t));
+  const long long step = (long long)gridDim.x * kEwThreads;
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n; i0 += step * kEwUnroll) {
+    float a[kEwUnroll], b[kEwUnroll], c[kEwUnroll], e[kEwUnroll], r[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n) { a[u] = jx[i * s_jx]; b[u] = jy[i * s_jy]; c[u] = ox[i * s_ox]; e[u] = oy[i * s_oy]; r[u] = rad[i * s_r]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n) {
+        const float dx = __fsub_rn(a[u], c[u]);
+        const float dy = __fsub_rn(b[u], e[u]);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        const float t = __fsub_rn(d, r[u]);
+        out[i] = torch_max(__fmul_rn(-a_in, t), __fmul_rn(-a_out, t));
+      }
+    }
   }
 }
 
@@ -92,23 +112,35 @@ __global__ void __launch_bounds__(kEwThreads) circle_backward_kernel(const float
                                                                     float a_out, const float* __restrict__ gout, float* __restrict__ d_jx,
                                                                     float* __restrict__ d_jy, float* __restrict__ d_ox,
                                                                     float* __restrict__ d_oy, float* __restrict__ d_r) {
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kEwThreads) {
-    const float dx = __fsub_rn(jx[i * s_jx], ox[i * s_ox]);
-    const float dy = __fsub_rn(jy[i * s_jy], oy[i * s_oy]);
-    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    const float t = __fsub_rn(d, rad[i * s_r]);
-    const float vi = __fmul_rn(-a_in, t), vo = __fmul_rn(-a_out, t);
-    // torch MaximumBackward: the larger branch gets the gradient, a tie splits it evenly
-    const float slope = (vi > vo) ? -a_in : ((vi < vo) ? -a_out : -0.5f * (a_in + a_out));
-    const float gt = gout[i] * slope;                     // d/dt
-    // d(t)/d(jx) = dx / d ; at the centre (d == 0) torch gives NaN, this library gives 0
-    const float ux = d > 0.f ? __fdiv_rn(dx, d) : 0.f;
-    const float uy = d > 0.f ? __fdiv_rn(dy, d) : 0.f;
-    if (d_jx) d_jx[i] = gt * ux;
-    if (d_jy) d_jy[i] = gt * uy;
-    if (d_ox) d_ox[i] = -gt * ux;
-    if (d_oy) d_oy[i] = -gt * uy;
-    if (d_r) d_r[i] = -gt;
+  const long long step = (long long)gridDim.x * kEwThreads;
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n; i0 += step * kEwUnroll) {
+    float a[kEwUnroll], b[kEwUnroll], c[kEwUnroll], e[kEwUnroll], r[kEwUnroll], go[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n) { a[u] = jx[i * s_jx]; b[u] = jy[i * s_jy]; c[u] = ox[i * s_ox]; e[u] = oy[i * s_oy]; r[u] = rad[i * s_r]; go[u] = gout[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i >= n) continue;
+      const float dx = __fsub_rn(a[u], c[u]);
+      const float dy = __fsub_rn(b[u], e[u]);
+      const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      const float t = __fsub_rn(d, r[u]);
+      const float vi = __fmul_rn(-a_in, t), vo = __fmul_rn(-a_out, t);
+      // torch MaximumBackward: the larger branch gets the gradient, a tie splits it evenly
+      const float slope = (vi > vo) ? -a_in : ((vi < vo) ? -a_out : -0.5f * (a_in + a_out));
+      const float gt = go[u] * slope;                       // d/dt
+      // d(t)/d(jx) = dx / d ; at the centre (d == 0) torch gives NaN, this library gives 0
+      const float ux = d > 0.f ? __fdiv_rn(dx, d) : 0.f;
+      const float uy = d > 0.f ? __fdiv_rn(dy, d) : 0.f;
+      if (d_jx) d_jx[i] = gt * ux;
+      if (d_jy) d_jy[i] = gt * uy;
+      if (d_ox) d_ox[i] = -gt * ux;
+      if (d_oy) d_oy[i] = -gt * uy;
+      if (d_r) d_r[i] = -gt;
+    }
   }
 }
 
@@ -117,14 +149,25 @@ __global__ void __launch_bounds__(kEwThreads) jl_forward_kernel(const float* __r
                                                                long long s_lo, const float* __restrict__ hi, long long s_hi, long long n,
                                                                float a_in, float a_out, float* __restrict__ out) {
   const float h_in = a_in * 0.5f, h_out = a_out * 0.5f;     // exact: the reference folds slope*0.5 before touching the tensor
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kEwThreads) {
-    const float l = lo[i * s_lo], h = hi[i * s_hi];
-    const float mid = __fdiv_rn(__fadd_rn(l, h), 2.0f);
-    const float rng = fabsf(__fsub_rn(h, l));
-    const float dev = fabsf(__fsub_rn(th[i * s_t], mid));
-    const float vin = __fsub_rn(__fmul_rn(a_in, dev), __fmul_rn(h_in, rng));
-    const float vout = __fsub_rn(__fmul_rn(a_out, dev), __fmul_rn(h_out, rng));
-    out[i] = torch_max(vin, vout);
+  const long long step = (long long)gridDim.x * kEwThreads;
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n; i0 += step * kEwUnroll) {
+    float l[kEwUnroll], h[kEwUnroll], t[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n) { l[u] = lo[i * s_lo]; h[u] = hi[i * s_hi]; t[u] = th[i * s_t]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i >= n) continue;
+      const float mid = __fdiv_rn(__fadd_rn(l[u], h[u]), 2.0f);
+      const float rng = fabsf(__fsub_rn(h[u], l[u]));
+      const float dev = fabsf(__fsub_rn(t[u], mid));
+      const float vin = __fsub_rn(__fmul_rn(a_in, dev), __fmul_rn(h_in, rng));
+      const float vout = __fsub_rn(__fmul_rn(a_out, dev), __fmul_rn(h_out, rng));
+      out[i] = torch_max(vin, vout);
+    }
   }
 }
 
@@ -135,21 +178,32 @@ __global__ void __launch_bounds__(kEwThreads) jl_backward_kernel(const float* __
                                                                 float a_in, float a_out, const float* __restrict__ gout,
                                                                 float* __restrict__ d_th, float* __restrict__ d_lo, float* __restrict__ d_hi) {
   const float h_in = a_in * 0.5f, h_out = a_out * 0.5f;
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kEwThreads) {
-    const float l = lo[i * s_lo], h = hi[i * s_hi];
-    const float mid = __fdiv_rn(__fadd_rn(l, h), 2.0f);
-    const float span = __fsub_rn(h, l);
-    const float u = __fsub_rn(th[i * s_t], mid);
-    const float dev = fabsf(u), rng = fabsf(span);
-    const float vin = __fsub_rn(__fmul_rn(a_in, dev), __fmul_rn(h_in, rng));
-    const float vout = __fsub_rn(__fmul_rn(a_out, dev), __fmul_rn(h_out, rng));
-    const float slope = (vin > vout) ? a_in : ((vin < vout) ? a_out : 0.5f * (a_in + a_out));
-    const float g = gout[i] * slope;
-    const float gu = g * sgn(u);                 // d/dtheta ; d/dmid = -gu
-    const float gr = -0.5f * g * sgn(span);      // through -slope*0.5*|hi-lo| : d/dhi = gr, d/dlo = -gr
-    if (d_th) d_th[i] = gu;
-    if (d_lo) d_lo[i] = -0.5f * gu - gr;
-    if (d_hi) d_hi[i] = -0.5f * gu + gr;
+  const long long step = (long long)gridDim.x * kEwThreads;
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n; i0 += step * kEwUnroll) {
+    float l[kEwUnroll], h[kEwUnroll], t[kEwUnroll], go[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n) { l[u] = lo[i * s_lo]; h[u] = hi[i * s_hi]; t[u] = th[i * s_t]; go[u] = gout[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long i = i0 + u * step;
+      if (i >= n) continue;
+      const float mid = __fdiv_rn(__fadd_rn(l[u], h[u]), 2.0f);
+      const float span = __fsub_rn(h[u], l[u]);
+      const float uu = __fsub_rn(t[u], mid);
+      const float dev = fabsf(uu), rng = fabsf(span);
+      const float vin = __fsub_rn(__fmul_rn(a_in, dev), __fmul_rn(h_in, rng));
+      const float vout = __fsub_rn(__fmul_rn(a_out, dev), __fmul_rn(h_out, rng));
+      const float slope = (vin > vout) ? a_in : ((vin < vout) ? a_out : 0.5f * (a_in + a_out));
+      const float g = go[u] * slope;
+      const float gu = g * sgn(uu);                // d/dtheta ; d/dmid = -gu
+      const float gr = -0.5f * g * sgn(span);      // through -slope*0.5*|hi-lo| : d/dhi = gr, d/dlo = -gr
+      if (d_th) d_th[i] = gu;
+      if (d_lo) d_lo[i] = -0.5f * gu - gr;
+      if (d_hi) d_hi[i] = -0.5f * gu + gr;
+    }
   }
 }
 
@@ -207,7 +261,7 @@ IklStatus ikl_circle_penalty_forward(const float* jx, int64_t s_jx, const float*
   if (n == 0) return IKL_OK;
   if (!jx || !jy || !ox || !oy || !radius || !out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
-  circle_forward_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(jx, s_jx, jy, s_jy, ox, s_ox, oy, s_oy, radius, s_r, n,
+  circle_forward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(jx, s_jx, jy, s_jy, ox, s_ox, oy, s_oy, radius, s_r, n,
                                                                               inside_slope, outside_slope, out);
   return cuda_status(cudaGetLastError());
 }
@@ -220,7 +274,7 @@ IklStatus ikl_circle_penalty_backward(const float* jx, int64_t s_jx, const float
   if (n == 0) return IKL_OK;
   if (!jx || !jy || !ox || !oy || !radius || !grad_out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
-  circle_backward_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(jx, s_jx, jy, s_jy, ox, s_ox, oy, s_oy, radius, s_r, n,
+  circle_backward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(jx, s_jx, jy, s_jy, ox, s_ox, oy, s_oy, radius, s_r, n,
                                                                                inside_slope, outside_slope, grad_out, d_jx, d_jy, d_ox,
                                                                                d_oy, d_radius);
   return cuda_status(cudaGetLastError());
@@ -232,7 +286,7 @@ IklStatus ikl_joint_limit_penalty_forward(const float* theta, int64_t s_t, const
   if (n == 0) return IKL_OK;
   if (!theta || !lo || !hi || !out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
-  jl_forward_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(theta, s_t, lo, s_lo, hi, s_hi, n, inside_slope, outside_slope, out);
+  jl_forward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(theta, s_t, lo, s_lo, hi, s_hi, n, inside_slope, outside_slope, out);
   return cuda_status(cudaGetLastError());
 }
 
@@ -243,7 +297,7 @@ IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, cons
   if (n == 0) return IKL_OK;
   if (!theta || !lo || !hi || !grad_out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
-  jl_backward_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(theta, s_t, lo, s_lo, hi, s_hi, n, inside_slope, outside_slope,
+  jl_backward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(theta, s_t, lo, s_lo, hi, s_hi, n, inside_slope, outside_slope,
                                                                            grad_out, d_theta, d_lo, d_hi);
   return cuda_status(cudaGetLastError());
 }
