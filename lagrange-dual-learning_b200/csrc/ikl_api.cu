@@ -230,6 +230,13 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
                   (!dyn || encode_planes(&p.tm_obst, in->obstacles, in->batch, 3, in->obst_sc, v.nobs, in->obst_so));
     }
   }
+  if (layout == kRows) {
+    // bulk-copy staged rows kernel: whole 512-row tiles of each tensor are single 16-byte aligned runs
+    const char* e = getenv("IKL_ROWS_TMA");
+    const bool want = !(e && e[0] == '0');
+    p.use_tma = want && in->batch >= kTmaTile && aligned16(in->theta) && aligned16(in->target) &&
+                (in->target_sb == 2 || in->target_sb == 3);
+  }
   const int forced = forced_layout();
   if (forced == kStrided) layout = kStrided;                 // the generic kernel accepts anything
   else if (forced >= 0 && forced != layout) return IKL_ERR_INVALID_ARGUMENT;   // tests: demand a fast layout or fail loudly

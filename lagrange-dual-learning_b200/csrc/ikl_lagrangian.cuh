@@ -184,12 +184,50 @@ struct WarpSharedAcc {
   }
   static constexpr int N = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : 16;      // vector length: next power of two >= K
   __device__ __forceinline__ void flush(f2 (&acc)[K]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float v[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = i < K ? f2_lo(acc[i]) + f2_hi(acc[i]) : 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) acc[i] = f2_splat(0.f);
+    reduce(v);
+  }
+  __device__ __forceinline__ void flush(float (&acc)[K]) {
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = i < K ? acc[i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = 0.f;
+    reduce(v);
+  }
+  // Rows pipeline: the thread keeps the sums of obstacle (k ^ r) in obstacle slot k (see run_rows_pipe); put them back
+  // in constraint order before the lanes (which have different r) are added together.
+  template <int OBASE>
+  __device__ __forceinline__ void flush_xor4(f2 (&acc)[K], int r) {
+    static_assert(K == OBASE + 12 && N == 16, "four obstacles x three tips");
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = i < K ? f2_lo(acc[i]) + f2_hi(acc[i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = f2_splat(0.f);
+#pragma unroll
+    for (int bit = 1; bit <= 2; bit <<= 1) {
+      const bool sw = (r & bit) != 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k & bit) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float a = v[OBASE + 3 * k + j], b = v[OBASE + 3 * (k | bit) + j];
+          v[OBASE + 3 * k + j] = sw ? b : a;
+          v[OBASE + 3 * (k | bit) + j] = sw ? a : b;
+        }
+      }
+    }
+    reduce(v);
+  }
+  // all 32 lanes of the warp must call this together
+  __device__ __forceinline__ void reduce(float (&v)[N]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // transposing steps: a lane keeps the half of the vector selected by its `off` bit and adds its partner's copy of it
     int idx = 0, off = 16;
 #pragma unroll
@@ -656,6 +694,192 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
   block_finalize<C::K>(p, s_warp);
 }
 
+// ---- rows layout, bulk-copy staged -------------------------------------------------------------------------------------
+// The reference's own tensors are contiguous per tile: 512 rows of theta (6 KiB), of q_ee_desired (4 or 6 KiB) and of
+// dynamic_obstacles (32 KiB) -- three one-dimensional bulk copies (SASS UBLKCP) per tile into the same barrier-free
+// pipeline as the planes kernel.  Thread t owns samples (t, t + 256) of the tile, like the direct-load rows kernel.
+// Shared-memory reads: theta / target rows are 3 (2) words apart -- conflict-free; an obstacle row is 16 words and a
+// sample 64 words, so the four LDS.128 of a sample are issued in the order k ^ r, r = (t >> 1) & 3, which spreads the
+// eight lanes of a quarter-warp over all 32 banks.  The thread therefore holds obstacle (k ^ r) in slot k; the maths is
+// symmetric in the obstacles except for the multiplier and the sum each term belongs to: multipliers come from a
+// per-r permuted table in shared memory, sums are put back in order when they are flushed (WarpSharedAcc::flush_xor4).
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class C>
+struct RowsTmaLayout {
+  static constexpr bool kSupported = C::J == 3 && (!C::DYN || C::NOBS == kMaxObst);
+  static constexpr int kThetaBytes = kTmaTile * 3 * 4;
+  static constexpr int kTargetBytes = kTmaTile * 3 * 4;                 // room for target rows of 2 or 3 floats
+  static constexpr int kObstBytes = C::DYN ? kTmaTile * 4 * kMaxObst * 4 : 0;
+  static constexpr int kStageBytes = kThetaBytes + kTargetBytes + kObstBytes;
+  static constexpr int kStages = IKL_TMA_STAGES;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
+  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);                  // index of the first obstacle constraint
+};
+
+template <class C, class W2>
+__device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, const W2& w2, WarpSharedAcc<C::K>& sacc, unsigned char* stage_mem,
+                                              unsigned long long* bars, int r) {
+  using L = RowsTmaLayout<C>;
+  constexpr int S = L::kStages;
+  const long long ntiles = p.batch / kTmaTile;       // full tiles only; the caller evaluates the ragged tail
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tg_sb = (int)p.tg_sb;                    // 2 or 3 (checked on the host)
+  const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
+  const unsigned drained0 = bar0 + 8 * S;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(drained0 + 8 * s, kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {      // one thread
+    const long long b0 = tile * kTmaTile;
+    const unsigned bar = bar0 + 8 * stage;
+    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
+    const unsigned tg_bytes = (unsigned)(kTmaTile * 4) * (unsigned)tg_sb;
+    mbar_expect_tx(bar, L::kThetaBytes + tg_bytes + L::kObstBytes);
+    bulk_g2s(dst, p.theta + b0 * 3, L::kThetaBytes, bar);
+    bulk_g2s(dst + L::kThetaBytes, p.target + b0 * tg_sb, tg_bytes, bar);
+    if (C::DYN) bulk_g2s(dst + L::kThetaBytes + L::kTargetBytes, p.obst + b0 * (4 * kMaxObst), L::kObstBytes, bar);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+
+  f2 acc[C::K];
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  auto flush = [&]() {
+    if constexpr (C::DYN) sacc.template flush_xor4<L::kObstBase>(acc, r);
+    else sacc.flush(acc);
+  };
+  int since_flush = 0, stage = 0;
+  unsigned parity = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar0 + 8 * stage, parity);
+    const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
+    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    const float* tA = reinterpret_cast<const float*>(st) + 3 * tid;
+    const float* tB = tA + 3 * kThreads;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) th[j] = f2_make(tA[j], tB[j]);
+    const float* gA = reinterpret_cast<const float*>(st + L::kThetaBytes) + tg_sb * tid;
+    const float* gB = gA + tg_sb * kThreads;
+    const f2 tx = f2_make(gA[0], gB[0]);
+    const f2 ty = f2_make(gA[1], gB[1]);
+    if constexpr (C::DYN) {
+      const float4* oA = reinterpret_cast<const float4*>(st + L::kThetaBytes + L::kTargetBytes) + kMaxObst * tid;
+      const float4* oB = oA + kMaxObst * kThreads;
+#pragma unroll
+      for (int k = 0; k < C::NOBS; ++k) {
+        const float4 a = oA[k ^ r], b4 = oB[k ^ r];
+        ob[k][0] = f2_make(a.x, b4.x);
+        ob[k][1] = f2_make(a.y, b4.y);
+        ob[k][2] = f2_make(a.z, b4.z);
+      }
+    } else {
+      static_obstacles_packed<C>(p, ob);
+    }
+    // hand the stage back: the last of the block's warps to get here refills it
+    __syncwarp();
+    if (lane == 0) {
+      const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
+      const long long next = tile + (long long)S * gridDim.x;
+      if (last && next < ntiles) {
+#if IKL_PIPE_PROXY_FENCE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+        issue(next, stage);
+      }
+    }
+    __syncwarp();
+    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    const long long bA = tile * kTmaTile + tid, bB = bA + kThreads;
+    if (C::GRAD) {
+      float* dA = p.dtheta + bA * 3;
+      float* dB = p.dtheta + bB * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dA[j] = f2_lo(dth[j]);
+        dB[j] = f2_hi(dth[j]);
+      }
+    } else {
+      store_side_outputs(p, bA, bB, ee, tx, ty);
+    }
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      flush();
+    }
+    if (++stage == S) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  flush();
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  using L = RowsTmaLayout<C>;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
+  __shared__ float2 s_lam_perm[4][kMaxK];      // multipliers as (w, w) pairs, obstacle entries permuted by k ^ r
+  __shared__ double s_warp[kWarps][kMaxK];
+  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
+  constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::MODE == kGradDevW);
+  if constexpr (kSmemWeights) {
+    if (threadIdx.x < 4 * kMaxK) {
+      const int rr = threadIdx.x / kMaxK, i = threadIdx.x % kMaxK;
+      int src = i;
+      if (C::DYN && i >= L::kObstBase && i < C::K) {
+        const int q = i - L::kObstBase, k = q / 3, j = q % 3;
+        src = L::kObstBase + 3 * (k ^ rr) + j;
+      }
+      float l = 0.f;
+      if (i < C::K) l = (C::MODE == kGradDevW) ? __ldg(p.w_dev + src) : p.u.w[src];
+      s_lam_perm[rr][i] = make_float2(l, l);
+    }
+  }
+  WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
+  if constexpr (kSmemWeights) run_rows_pipe<C>(p, PackedSmemWeights{s_lam_perm[r]}, sacc, dyn_smem, bars, r);
+  else run_rows_pipe<C>(p, PackedHostWeights{p.pu}, sacc, dyn_smem, bars, r);
+  // ragged tail (< 512 samples), one sample per thread through the scalar code
+  {
+    const long long full = (p.batch / kTmaTile) * kTmaTile;
+    float sacc1[C::K];
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) sacc1[i] = 0.f;
+    auto tail = [&](const auto& w) {
+      for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
+        float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3];
+        if (!C::DYN) static_obstacles<C>(p, ob);
+        load_sample<C>(p, b, th, tx, ty, ob);
+        eval_sample<3, C::NOBS, C::JL, C::GRAD, true>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
+        store_sample<C>(p, b, dth, ee, tx, ty);
+      }
+    };
+    if (full < p.batch) {
+      if constexpr (C::MODE == kGradDevW) tail(DeviceWeights<C::K>(p.u, p.w_dev));
+      else tail(HostWeights(p.u, nullptr));
+    }
+    sacc.flush(sacc1);
+  }
+  block_finalize<C::K>(p, s_warp);
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
   __shared__ SharedAcc<C::K> sacc;
@@ -723,6 +947,29 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       set_last_kernel_name(name);
       count_launch();
       lagrangian_planes_tma_kernel<C><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
+  if constexpr (C::LAYOUT == kRows && RowsTmaLayout<C>::kSupported) {
+    if (p.use_tma) {
+      static int rows_blocks_per_sm = 0;
+      constexpr size_t smem = RowsTmaLayout<C>::kSmemBytes;
+      if (rows_blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(lagrangian_rows_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_rows_tma_kernel<C>, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        rows_blocks_per_sm = n > 0 ? n : 1;
+      }
+      long long tiles = p.batch / kTmaTile;
+      if (tiles < 1) tiles = 1;
+      long long grid = (long long)grid_sms() * rows_blocks_per_sm;
+      if (grid > tiles) grid = tiles;
+      if (grid > max_blocks) grid = max_blocks;
+      set_last_kernel_name(name);
+      count_launch();
+      lagrangian_rows_tma_kernel<C><<<(unsigned)grid, kThreads, smem, stream>>>(p);
       return cudaGetLastError();
     }
   }

@@ -15,7 +15,8 @@ cudaError_t launch_mode(const Variant& v, const LagrangianParams& p, cudaStream_
   constexpr bool UNIT = IKL_FAMILY_UNIT;
   static thread_local char name[96];
   static const char* const layout_names[] = {"strided", "rows", "planes"};
-  const char* lname = (L == kPlanes && p.use_tma) ? "planes_tma" : layout_names[L];
+  const bool rows_tma = L == kRows && p.use_tma && RowsTmaLayout<Cfg<L, J, NOBS, DYN, JL, kFwd, UNIT>>::kSupported;
+  const char* lname = (L == kPlanes && p.use_tma) ? "planes_tma" : (rows_tma ? "rows_tma" : layout_names[L]);
   static const char* const mode_names[] = {"fwd", "fwdbwd_hostw", "fwdbwd_devw"};
   snprintf(name, sizeof(name), "ikl_lagrangian<%s,J%d,obs%d,%s,%s,%s,%s>", lname, J, NOBS, DYN ? "dyn" : "stat",
            JL ? "jl" : "nojl", mode_names[v.mode], UNIT ? "unit" : "len");

@@ -356,10 +356,13 @@ def test_tma_pipeline_ragged_tiles_all_configs(B, cuda_device, monkeypatch):
     assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][0], results[1][0])
     viol_f, _, _, kname = run_layout("planes", spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
     assert "<planes_tma," in kname and np.array_equal(viol_f, results[0][0])
-    # the same samples in the reference's row-major layout: identical gradient on the full 512-sample tiles
-    viol_r, _, dth_r, _ = run_layout("rows", spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    # the same samples in the reference's row-major layout, direct-load kernel: identical gradient on the full 512-sample
+    # tiles (same packed maths, same order); the staged rows kernel adds the obstacle forces in a different order
+    monkeypatch.setenv("IKL_ROWS_TMA", "0")
+    viol_r, _, dth_r, kname = run_layout("rows", spec, theta, q_des, obst, lam.tolist(), True, monkeypatch)
+    monkeypatch.delenv("IKL_ROWS_TMA")
     full = (B // 512) * 512
-    assert np.array_equal(dth_r[:full], results[0][1][:full])
+    assert "<rows," in kname and np.array_equal(dth_r[:full], results[0][1][:full])
     assert np.all(np.abs(viol_r - results[0][0]) <= 2e-6 * abs_sums + 1e-30)
 
 
@@ -388,6 +391,52 @@ def test_tma_pipeline_padded_and_irregular_plane_strides(cuda_device, monkeypatc
   v1, l1, d1 = fused.lagrangian_forward_backward(spec, thp, tgp, obp, lam, dtheta=dth)
   assert "<planes_tma," in _cabi.last_kernel_name()
   assert torch.equal(v1, v0) and torch.equal(d1.contiguous(), d0) and float(l1) == float(l0)
+
+
+@pytest.mark.parametrize("B", [512, 1024 + 37, 151556 + 3])
+def test_rows_bulk_copy_pipeline(B, cuda_device, monkeypatch):
+  """The staged rows kernel (three bulk copies per 512-row tile, obstacle rows read in the bank-conflict-free order k ^ r,
+  permuted multiplier table, sums un-permuted at the flush) against the oracle and against the direct-load rows kernel:
+  every config, host / device multipliers, forward-only, two-column targets, and an unaligned view that must fall back."""
+  from ikl import fused, synthetic, _cabi
+  dev = cuda_device
+  theta, q_des, obst = synthetic.make_batch(B, seed=2000 + B)
+  th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+  for name in CONFIG_NAMES:
+    spec, ospec = specs_for(name)
+    K = spec.num_constraints
+    lam = (0.3 + 0.2 * np.arange(K)).astype(np.float32)          # all different: a permutation mistake cannot hide
+    sums64, abs_sums, dth64, kink, truth = oracle_truth(ospec, theta, q_des, obst, lam)
+    o = ob if spec.dynamic else None
+    monkeypatch.setenv("IKL_ROWS_TMA", "0")
+    v_ref, l_ref, d_ref = fused.lagrangian_forward_backward(spec, th, qd, o, lam.tolist())
+    assert "<rows," in _cabi.last_kernel_name()
+    v_ref, d_ref = v_ref.clone(), d_ref.clone()
+    monkeypatch.delenv("IKL_ROWS_TMA")
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(dev)):
+      v, l, d = fused.lagrangian_forward_backward(spec, th, qd, o, weights)
+      assert "<rows_tma," in _cabi.last_kernel_name(), _cabi.last_kernel_name()
+      if spec.dynamic:      # obstacle forces are added in the order k ^ r: equal to round-off, not bit for bit
+        assert float((d - d_ref).abs().max()) <= 1e-6 * float(d_ref.abs().max()), name
+      else:
+        assert torch.equal(d, d_ref), name
+      assert np.all(np.abs(v.cpu().numpy() - sums64) <= RTOL * abs_sums + 1e-30), name
+      assert np.all(np.abs((v - v_ref).cpu().numpy()) <= 2e-6 * abs_sums + 1e-30), name
+      grad_close(d.cpu().numpy(), dth64, truth)
+    out = fused.lagrangian_forward(spec, th, qd, o, lam.tolist())
+    assert "<rows_tma," in _cabi.last_kernel_name() and torch.equal(out["constraint_violations"], v)
+    # q_ee_desired as a contiguous (B,2) tensor: 8-byte rows
+    v2, _, d2 = fused.lagrangian_forward_backward(spec, th, qd[:, :2].contiguous(), o, lam.tolist())
+    assert "<rows_tma," in _cabi.last_kernel_name() and torch.equal(d2, d) and torch.equal(v2, v)
+  # a view that starts 12 bytes into its allocation cannot be bulk-copied: direct-load rows kernel, same numbers
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  lam = [0.5 + 0.1 * i for i in range(16)]
+  v_a, _, d_a = fused.lagrangian_forward_backward(spec, th[1:], qd[1:], ob[1:], lam)
+  assert "<rows," in _cabi.last_kernel_name()
+  v_b, _, d_b = fused.lagrangian_forward_backward(spec, th[1:].clone(), qd[1:].clone(), ob[1:].clone(), lam)
+  assert ("<rows_tma," if B - 1 >= 512 else "<rows,") in _cabi.last_kernel_name()
+  assert float((d_a - d_b).abs().max()) <= 1e-6 * float(d_a.abs().max())
+  assert float((v_a - v_b).abs().max()) <= 2e-6 * float(v_a.abs().max())
 
 
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
@@ -540,11 +589,16 @@ def test_full_size_properties(cuda_device, monkeypatch):
   assert float((parts - v1.double()).abs().max()) <= 1e-5 * float(v1.abs().max()) + 1e-9 * abs_bound
   v1b, _, d1b = fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam1.tolist())
   assert torch.equal(v1b, v1) and torch.equal(d1b, d1), "launches are deterministic"
-  # (c) layout independence: planes give the same per-sample gradient bits and the same sums to round-off
+  # (c) layout independence: planes give the same sums and gradients to round-off as the staged rows kernel (which adds
+  # the obstacle forces in a different order), and the same per-sample gradient BITS as the direct-load rows kernel
   thp, tgp, obp = synthetic.to_planes(theta, q_des, obst)
   vp, lp, dp = fused.lagrangian_forward_backward(spec, thp, tgp, obp, lam1.tolist())
-  assert torch.equal(dp.contiguous(), d1.contiguous())
+  assert float((dp.contiguous() - d1).abs().max()) <= 1e-6 * scale
   assert float((vp - v1).abs().max()) <= 1e-6 * float(v1.abs().max())
+  monkeypatch.setenv("IKL_ROWS_TMA", "0")
+  vd, _, dd = fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam1.tolist())
+  monkeypatch.delenv("IKL_ROWS_TMA")
+  assert torch.equal(dp.contiguous(), dd.contiguous())
   # (d) oracle spot checks on slices of the big batch
   for s in (0, 5_000_000, B - 4096):
     sl = slice(s, s + 4096)
@@ -576,8 +630,12 @@ def test_layout_dispatch_on_views_and_alignments(cuda_device, monkeypatch):
     v, l, d = fused.lagrangian_forward_backward(spec, th, qd, ob, lam)
     return v.clone(), d.contiguous().clone(), _cabi.last_kernel_name()
 
+  monkeypatch.setenv("IKL_ROWS_TMA", "0")
   v0, d0, k0 = run(theta, q_des, obst)
+  monkeypatch.delenv("IKL_ROWS_TMA")
   assert "<rows," in k0
+  vt, dt, kt = run(theta, q_des, obst)             # staged rows kernel: same numbers to round-off
+  assert "<rows_tma," in kt and float((dt - d0).abs().max()) <= 1e-6 * float(d0.abs().max())
   # planes, multiple of 4 and aligned -> bulk-async kernel
   thp, tgp, obp = synthetic.to_planes(theta, q_des, obst)
   v1, d1, k1 = run(thp, tgp, obp)
@@ -606,7 +664,7 @@ def test_layout_dispatch_on_views_and_alignments(cuda_device, monkeypatch):
   assert near(d4, d0[1:-1])
   # odd batch of rows: packed tiles + scalar tail
   v5, d5, k5 = run(theta[:-1], q_des[:-1], obst[:-1])
-  assert "<rows," in k5 and torch.equal(d5[:4096 - 0], d0[:4096]) and near(d5, d0[:-1])
+  assert "<rows_tma," in k5 and torch.equal(d5[:4096], dt[:4096]) and near(d5, d0[:-1])
   # q_ee_desired with only two columns, non-contiguous theta (every other row of a bigger tensor)
   big = torch.zeros(2 * B, 3, device=dev)
   big[::2] = theta

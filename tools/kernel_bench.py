@@ -110,6 +110,52 @@ def measure_elementwise(args):
                       "note": "includes the torch allocation of the output; strided column views read whole sectors"}), flush=True)
 
 
+def measure_callers(args):
+  """Rows f-1 / f-2 of SURVEY 8: on-device dataset generation and evaluation statistics (the steps either side of the path)."""
+  import torch
+  from ikl import ConstraintSpec, standard_config, synthetic, device_data, _cabi
+  peak = 6548.8
+  try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+  except Exception:
+    pass
+  B = 1 << args.batch_log2
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  for cfg_name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static"):
+    cfg = standard_config(cfg_name)
+    device_data.generate_dataset(cfg, B, seed=1, device="cuda:0")
+    torch.cuda.synchronize()
+    ev0.record()
+    for rep in range(3):
+      d = device_data.generate_dataset(cfg, B, seed=2 + rep, device="cuda:0")
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 3
+    out_bytes = 24 + (64 if d["random_obstacles"] is not None else 0)       # theta 12 + ee 12 (+ obstacle rows 64) written per example
+    print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "kernel": "dataset_generate (f-1) " + cfg_name, "ms_mean": round(ms, 4),
+                      "gsamples_per_s": round(B / ms / 1e6, 3), "algo_GBps": round(out_bytes * B / ms / 1e6, 1),
+                      "frac_of_hbm_peak": round(out_bytes * B / ms / 1e6 / peak, 4), "exhausted": int(d["exhausted"].item()),
+                      "note": "Philox + FK + rejection sampling per example, includes the torch allocation of the outputs; "
+                              "reference: 6.2 s per 8000 examples on the host (SURVEY 8f-1)"}), flush=True)
+    del d
+  theta, q_des, obst = synthetic.make_batch(B, seed=0, device="cuda:0")
+  spec = ConstraintSpec.from_config(standard_config("cfg_joint_limits_and_4obs_dynamic"), 3, 0.005, 1.0)
+  for lname, (th, tg, ob) in (("planes", synthetic.to_planes(theta, q_des, obst)), ("rows", (theta, q_des, obst))):
+    counts, pos = device_data.eval_stats(spec, th, tg, ob)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.iters):
+      device_data.eval_stats(spec, th, tg, ob, counts=counts, pos_err_sum=pos)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.iters
+    print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "kernel": "eval_stats (f-2) " + lname, "ms_mean": round(ms, 4),
+                      "gsamples_per_s": round(B / ms / 1e6, 2), "algo_GBps": round(68 * B / ms / 1e6, 1),
+                      "frac_of_hbm_peak": round(68 * B / ms / 1e6 / peak, 4),
+                      "note": "per-constraint violation counts + any-JL / any-obstacle rates + position error; 68 algorithmic bytes per sample"}),
+          flush=True)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--batch-log2", type=int, default=24)
@@ -124,6 +170,7 @@ def main():
     measure(args)
     if not args.quick and not args.configs and not args.layouts:
       measure_elementwise(args)
+      measure_callers(args)
     return
   for lib in args.libs.split(","):
     env = dict(os.environ, IKL_LIB=os.path.join(PKG, "lib", lib) if not os.path.isabs(lib) else lib)
