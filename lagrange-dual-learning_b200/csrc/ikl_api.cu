@@ -184,40 +184,27 @@ int detect_layout(const IklSpec* spec, const IklBatch* in, bool grad, const floa
   return kStrided;
 }
 
-IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
-              double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
-              void* stream) {
-  IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
-  if (st != IKL_OK) return st;
-  if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
+}  // namespace
 
-  LagrangianParams p;
+int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const float* w_host, bool grad, float* dtheta, int64_t dt_sb,
+                              int64_t dt_sj, LagrangianParams& p, Variant& v) {
   memset(&p, 0, sizeof(p));
-  fill_uniforms(spec, w->host, p.u);
+  fill_uniforms(spec, w_host, p.u);
   fill_packed_uniforms(spec, p.u, p.pu);
   p.batch = in->batch;
   p.theta = in->theta;    p.th_sb = in->theta_sb;  p.th_sj = in->theta_sj;
   p.target = in->target;  p.tg_sb = in->target_sb; p.tg_sc = in->target_sc;
   p.obst = in->obstacles; p.ob_sb = in->obst_sb;   p.ob_so = in->obst_so;  p.ob_sc = in->obst_sc;
   p.dtheta = dtheta;      p.dt_sb = dt_sb;         p.dt_sj = dt_sj;
-  p.q_ee = q_ee_out;
-  p.err_sq = err_sq_out;
-  p.w_dev = w->device;
-  p.partials = reinterpret_cast<double*>(workspace);
-  p.counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + kPartialsBytes);
-  p.viol_out = viol_out;
-  p.loss_out = loss_out;
-  p.viol_accum = viol_accum;
 
-  Variant v;
   v.nobs = spec->num_obstacles;
   v.dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles != 0;
   v.jl = spec->enforce_joint_limits != 0;
-  v.mode = !grad ? kFwd : (w->host ? kGradHostW : kGradDevW);
+  v.mode = kFwd;
 
   int layout = detect_layout(spec, in, grad, dtheta, dt_sb, dt_sj);
   if (layout == kPlanes) {
-    // the bulk-async staged kernel moves whole 16-byte multiples: batch % 4 == 0 and 16-byte aligned planes
+    // the TMA-staged kernel describes the planes as tensors: batch % 4 == 0, 16-byte aligned planes, strides % 4 == 0
     const bool dyn = v.dyn;
     const char* e = getenv("IKL_PLANES_TMA");
     const bool want = !(e && e[0] == '0');
@@ -239,8 +226,34 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   }
   const int forced = forced_layout();
   if (forced == kStrided) layout = kStrided;                 // the generic kernel accepts anything
-  else if (forced >= 0 && forced != layout) return IKL_ERR_INVALID_ARGUMENT;   // tests: demand a fast layout or fail loudly
+  else if (forced >= 0 && forced != layout) return -(int)IKL_ERR_INVALID_ARGUMENT;   // tests: demand a fast layout or fail loudly
+  return layout;
+}
 
+namespace {
+
+IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
+              double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
+              void* stream) {
+  IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
+  if (st != IKL_OK) return st;
+  if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
+
+  LagrangianParams p;
+  Variant v;
+  const int layout = prepare_lagrangian_params(spec, in, w->host, grad, dtheta, dt_sb, dt_sj, p, v);
+  if (layout < 0) return (IklStatus)(-layout);
+  v.mode = !grad ? kFwd : (w->host ? kGradHostW : kGradDevW);
+  p.q_ee = q_ee_out;
+  p.err_sq = err_sq_out;
+  p.w_dev = w->device;
+  p.partials = reinterpret_cast<double*>(workspace);
+  p.counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + kPartialsBytes);
+  p.viol_out = viol_out;
+  p.loss_out = loss_out;
+  p.viol_accum = viol_accum;
+
+  const int forced = forced_layout();
   cudaStream_t cs = (cudaStream_t)stream;
   bool found = false;
   cudaError_t e = cudaSuccess;

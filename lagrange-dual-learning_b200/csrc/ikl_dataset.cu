@@ -12,6 +12,7 @@
 
 #include "ikl_common.h"
 #include "ikl_device.cuh"
+#include "ikl_lagrangian.cuh"
 
 namespace ikl {
 namespace {
@@ -233,6 +234,26 @@ IklStatus ikl_eval_stats(const IklSpec* spec, const IklBatch* in, float threshol
   if (in->batch == 0) return IKL_OK;
   const bool dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles;
   if (!in->theta || !in->target || (dyn && !in->obstacles)) return IKL_ERR_INVALID_ARGUMENT;
+  {
+    // the reference's own tensors or planes: same staged pipelines as the Lagrangian kernels
+    LagrangianParams lp;
+    Variant v;
+    const int layout = prepare_lagrangian_params(spec, in, nullptr, false, nullptr, 0, 0, lp, v);
+    if (layout < 0) return (IklStatus)(-layout);
+    if ((layout == kRows || layout == kPlanes) && lp.use_tma) {
+      lp.stats_threshold = threshold;
+      lp.stats_counts = reinterpret_cast<unsigned long long*>(counts_out);
+      lp.stats_pos_err = pos_err_sum_out;
+      bool found = false;
+      const cudaError_t e = layout == kRows ? launch_stats_family<kRows>(v, lp, (cudaStream_t)stream, 2048, &found)
+                                            : launch_stats_family<kPlanes>(v, lp, (cudaStream_t)stream, 2048, &found);
+      if (found) {
+        set_last_kernel_name(layout == kRows ? "ikl_eval_stats<rows_tma>" : "ikl_eval_stats<planes_tma>");
+        return cuda_status(e);
+      }
+    }
+  }
+  set_last_kernel_name("ikl_eval_stats<strided>");
   StatsParams p;
   memset(&p, 0, sizeof(p));
   for (int m = 0; m < kMaxLinks; ++m) p.u.link[m] = spec->link_length[m];

@@ -16,6 +16,8 @@
 //             8-byte access -- the loaded register pair IS the packed operand -- and stores d/dtheta the same way
 #pragma once
 
+#include <type_traits>
+
 #include "ikl_common.h"
 #include "ikl_device.cuh"
 #include "ikl_packed.cuh"
@@ -65,6 +67,10 @@ struct LagrangianParams {
   // TMA descriptors of the planes as 2-D / 3-D tensors (sample index innermost), encoded by the host per call:
   // theta {B, 3}, target {B, 2}, obstacles {B, 3, n}; box = 256 samples x every plane of the group.
   TensorMap tm_theta, tm_target, tm_obst;
+  // evaluation statistics (stats_*_tma_kernel): counts[0..K) = #(term > threshold), [16] any joint limit, [17] any obstacle
+  float stats_threshold;
+  unsigned long long* stats_counts;
+  double* stats_pos_err;
 };
 static_assert(sizeof(LagrangianParams) <= 4096, "kernel parameter block too large");
 
@@ -553,6 +559,156 @@ struct TmaLayout {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
 };
 
+// ---- what a pipeline does with a pair of samples ----------------------------------------------------------------------
+// The two staged pipelines (run_planes_pipe, run_rows_pipe) hand every pair of samples to a "body":
+//   pair(th, tx, ty, ob, bA, bB)   operands of samples bA and bB (packed: lo half = bA, hi half = bB)
+//   tile_done()                    once per tile, by every thread of the block (also by threads without a valid pair)
+//   finish()                       after the last tile
+// LagrangianBody: the K running sums (+ d/dtheta).  `r`: the rows pipeline keeps obstacle (k ^ r) in slot k.
+template <class C, class W2>
+struct LagrangianBody {
+  const LagrangianParams& p;
+  const W2& w2;
+  WarpSharedAcc<C::K>& sacc;
+  const int r;
+  f2 acc[C::K];
+  int since_flush;
+  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
+  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
+  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, WarpSharedAcc<C::K>& sa, int rr)
+      : p(pp), w2(w), sacc(sa), r(rr), since_flush(0) {
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  }
+  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
+    f2 dth[3], ee[3];
+    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    if (C::GRAD) {
+      if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
+#pragma unroll
+        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + bA, dth[j]);
+      } else {
+        float* dA = p.dtheta + bA * 3;
+        float* dB = p.dtheta + bB * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          dA[j] = f2_lo(dth[j]);
+          dB[j] = f2_hi(dth[j]);
+        }
+      }
+    } else {
+      store_side_outputs(p, bA, bB, ee, tx, ty);
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if constexpr (kPermuted) sacc.template flush_xor4<kObstBase>(acc, r);
+    else sacc.flush(acc);
+  }
+  __device__ __forceinline__ void tile_done() {
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      flush();
+    }
+  }
+  __device__ __forceinline__ void finish() { flush(); }
+};
+
+// StatsBody: the evaluation statistics of scripts/evaluation/visualize_ik_solutions.py:97-119 (reference) -- per-constraint
+// counts of per-sample terms above a threshold, samples violating any joint limit / any obstacle (term > 0) and the
+// summed end-effector error sqrt(sum(position_err_sq)).  Same per-sample maths as the Lagrangian (eval_pair with fresh sums).
+constexpr int kStatSlots = kMaxK + 2;
+template <class C>
+struct StatsBody {
+  const LagrangianParams& p;
+  const int r;
+  unsigned cnt[C::K];
+  unsigned any_jl, any_ob;
+  double err;
+  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
+  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
+  __device__ __forceinline__ StatsBody(const LagrangianParams& pp, int rr) : p(pp), r(rr), any_jl(0), any_ob(0), err(0.0) {
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) cnt[i] = 0;
+  }
+  __device__ __forceinline__ void add(const float (&v)[C::K]) {
+    float mjl = -1.f, mob = -1.f;
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) {
+      cnt[i] += v[i] > p.stats_threshold;
+      if (C::JL && i >= 1 && i < 4) mjl = fmaxf(mjl, v[i]);
+      if (i >= kObstBase) mob = fmaxf(mob, v[i]);
+    }
+    any_jl += mjl > 0.f;
+    any_ob += mob > 0.f;
+    err += (double)__fsqrt_rn(v[0]);      // sqrt(position_err_sq.sum()) with position_err_sq = 0.5*e^2: the reference's |e|/sqrt(2)
+  }
+  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long, long long) {
+    f2 acc[C::K], dth[3], ee[3];
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+    const PackedHostWeights w2{p.pu};
+    eval_pair<C::NOBS, C::JL, false>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    float v[C::K];
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
+    add(v);
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) v[i] = f2_hi(acc[i]);
+    add(v);
+  }
+  __device__ __forceinline__ void tile_done() {}
+  // after the last tile: put the obstacle counters back in constraint order (rows pipeline), so that the caller can add
+  // tail samples in plain order before commit()
+  __device__ __forceinline__ void finish() {
+    if constexpr (kPermuted) {
+#pragma unroll
+      for (int bit = 1; bit <= 2; bit <<= 1) {
+        const bool sw = (r & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k & bit) continue;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const unsigned a = cnt[kObstBase + 3 * k + j], b = cnt[kObstBase + 3 * (k | bit) + j];
+            cnt[kObstBase + 3 * k + j] = sw ? b : a;
+            cnt[kObstBase + 3 * (k | bit) + j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  // warp sums -> the block's shared counters (s_counts zeroed by the caller before the pipeline's first barrier)
+  __device__ __forceinline__ void commit(unsigned* s_counts, double* s_err) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) {
+      const unsigned v = __reduce_add_sync(0xffffffffu, cnt[i]);
+      if (lane == 0 && v) atomicAdd(&s_counts[i], v);
+    }
+    const unsigned vj = __reduce_add_sync(0xffffffffu, any_jl), vo = __reduce_add_sync(0xffffffffu, any_ob);
+    double e = err;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if (lane == 0) {
+      if (vj) atomicAdd(&s_counts[kMaxK], vj);
+      if (vo) atomicAdd(&s_counts[kMaxK + 1], vo);
+      s_err[threadIdx.x >> 5] = e;
+    }
+  }
+};
+
+// block totals -> global (64-bit counters, fp64 error sum)
+__device__ __forceinline__ void stats_block_finalize(const LagrangianParams& p, const unsigned* s_counts, const double* s_err) {
+  __syncthreads();
+  if (threadIdx.x < kStatSlots && s_counts[threadIdx.x]) atomicAdd(p.stats_counts + threadIdx.x, (unsigned long long)s_counts[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    double e = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < kWarps; ++wq) e += s_err[wq];
+    atomicAdd(p.stats_pos_err, e);
+  }
+}
+
 // Arrive on an mbarrier (release: the caller's shared-memory reads are performed first) and report whether this was the
 // arrival that completed the phase: the returned state is the one BEFORE the arrival, so a pending count of 1 means "last".
 __device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
@@ -570,9 +726,8 @@ __device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
 // issues the TMA loads of the tile that goes there next.  Nobody waits for anybody, only for data.  (Round-1 history,
 // profiles/r01/README.md: with 17 one-dimensional bulk copies per tile the issuing warp ran ~45 % more instructions than
 // its siblings and throttled the block whichever warp it was; six UTMALDG make the refill cheap enough to hand around.)
-template <class C, class W2, class Acc>
-__device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const W2& w2, Acc& sacc, unsigned char* stage_mem,
-                                                unsigned long long* bars) {
+template <class C, class Body>
+__device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars) {
   using L = TmaLayout<C>;
   constexpr int S = L::kStages;
   static_assert(kThreads == kTmaBox, "thread v of a 512-sample tile owns samples (2v, 2v+1): half = v / 128");
@@ -615,16 +770,13 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const
     }
   }
 
-  f2 acc[C::K];
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  int since_flush = 0, stage = 0;
+  int stage = 0;
   unsigned parity = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar0 + 8 * stage, parity);
     const long long b = tile * kTmaTile + 2 * tid;
     const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
-    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    f2 th[3], ob[C::NOB][3];
     int pl = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
@@ -653,32 +805,20 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, const
       }
     }
     __syncwarp();
-    if (b < B) {
-      eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
-      if (C::GRAD) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
-      } else {
-        store_side_outputs(p, b, b + 1, ee, tx, ty);
-      }
-    }
-    if (++since_flush == kFlushSamples / 2) {
-      since_flush = 0;
-      sacc.flush(acc);
-    }
+    if (b < B) body.pair(th, tx, ty, ob, b, b + 1);
+    body.tile_done();
     if (++stage == S) {
       stage = 0;
       parity ^= 1u;
     }
   }
-  sacc.flush(acc);
+  body.finish();
 }
 
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   using L = TmaLayout<C>;
-  unsigned char* stage_mem = dyn_smem;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
   __shared__ float2 s_lam2[kMaxK];
   __shared__ double s_warp[kWarps][kMaxK];
@@ -689,8 +829,12 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
     }
   }
   WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
-  if constexpr (C::MODE == kGradDevW) run_planes_pipe<C>(p, PackedSmemWeights{s_lam2}, sacc, stage_mem, bars);
-  else run_planes_pipe<C>(p, PackedHostWeights{p.pu}, sacc, stage_mem, bars);
+  auto run = [&](const auto& w2) {
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, 0);
+    run_planes_pipe<C>(p, body, dyn_smem, bars);
+  };
+  if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
+  else run(PackedHostWeights{p.pu});
   block_finalize<C::K>(p, s_warp);
 }
 
@@ -720,9 +864,8 @@ struct RowsTmaLayout {
   static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);                  // index of the first obstacle constraint
 };
 
-template <class C, class W2>
-__device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, const W2& w2, WarpSharedAcc<C::K>& sacc, unsigned char* stage_mem,
-                                              unsigned long long* bars, int r) {
+template <class C, class Body>
+__device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars, int r) {
   using L = RowsTmaLayout<C>;
   constexpr int S = L::kStages;
   const long long ntiles = p.batch / kTmaTile;       // full tiles only; the caller evaluates the ragged tail
@@ -759,19 +902,12 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, const W
     }
   }
 
-  f2 acc[C::K];
-#pragma unroll
-  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  auto flush = [&]() {
-    if constexpr (C::DYN) sacc.template flush_xor4<L::kObstBase>(acc, r);
-    else sacc.flush(acc);
-  };
-  int since_flush = 0, stage = 0;
+  int stage = 0;
   unsigned parity = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar0 + 8 * stage, parity);
     const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
-    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    f2 th[3], ob[C::NOB][3];
     const float* tA = reinterpret_cast<const float*>(st) + 3 * tid;
     const float* tB = tA + 3 * kThreads;
 #pragma unroll
@@ -806,29 +942,15 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, const W
       }
     }
     __syncwarp();
-    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
-    const long long bA = tile * kTmaTile + tid, bB = bA + kThreads;
-    if (C::GRAD) {
-      float* dA = p.dtheta + bA * 3;
-      float* dB = p.dtheta + bB * 3;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        dA[j] = f2_lo(dth[j]);
-        dB[j] = f2_hi(dth[j]);
-      }
-    } else {
-      store_side_outputs(p, bA, bB, ee, tx, ty);
-    }
-    if (++since_flush == kFlushSamples / 2) {
-      since_flush = 0;
-      flush();
-    }
+    const long long bA = tile * kTmaTile + tid;
+    body.pair(th, tx, ty, ob, bA, bA + kThreads);
+    body.tile_done();
     if (++stage == S) {
       stage = 0;
       parity ^= 1u;
     }
   }
-  flush();
+  body.finish();
 }
 
 template <class C>
@@ -854,8 +976,12 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_
     }
   }
   WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
-  if constexpr (kSmemWeights) run_rows_pipe<C>(p, PackedSmemWeights{s_lam_perm[r]}, sacc, dyn_smem, bars, r);
-  else run_rows_pipe<C>(p, PackedHostWeights{p.pu}, sacc, dyn_smem, bars, r);
+  auto run = [&](const auto& w2) {
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, r);
+    run_rows_pipe<C>(p, body, dyn_smem, bars, r);
+  };
+  if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]});
+  else run(PackedHostWeights{p.pu});
   // ragged tail (< 512 samples), one sample per thread through the scalar code
   {
     const long long full = (p.batch / kTmaTile) * kTmaTile;
@@ -878,6 +1004,48 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_
     sacc.flush(sacc1);
   }
   block_finalize<C::K>(p, s_warp);
+}
+
+// ---- evaluation statistics through the same pipelines -------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) stats_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  using L = TmaLayout<C>;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
+  __shared__ unsigned s_counts[kStatSlots];
+  __shared__ double s_err[kWarps];
+  if (threadIdx.x < kStatSlots) s_counts[threadIdx.x] = 0;      // ordered by the pipeline's first block barrier
+  StatsBody<C> body(p, 0);
+  run_planes_pipe<C>(p, body, dyn_smem, bars);
+  body.commit(s_counts, s_err);
+  stats_block_finalize(p, s_counts, s_err);
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) stats_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  using L = RowsTmaLayout<C>;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
+  __shared__ unsigned s_counts[kStatSlots];
+  __shared__ double s_err[kWarps];
+  if (threadIdx.x < kStatSlots) s_counts[threadIdx.x] = 0;
+  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
+  StatsBody<C> body(p, r);
+  run_rows_pipe<C>(p, body, dyn_smem, bars, r);
+  // ragged tail (< 512 rows), one sample per thread through the scalar code
+  const long long full = (p.batch / kTmaTile) * kTmaTile;
+  const HostWeights w(p.u, nullptr);
+  for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
+    float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3], acc[C::K];
+    if (!C::DYN) static_obstacles<C>(p, ob);
+    load_sample<C>(p, b, th, tx, ty, ob);
+#pragma unroll
+    for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
+    eval_sample<3, C::NOBS, C::JL, false, true>(p.u, w, th, tx, ty, ob, acc, dth, ee);
+    body.add(acc);
+  }
+  body.commit(s_counts, s_err);
+  stats_block_finalize(p, s_counts, s_err);
 }
 
 template <class C>
@@ -1002,5 +1170,37 @@ struct Variant {
 // Instantiated once per family in ikl_lagrangian_<family>.cu.
 template <int LAYOUT, int J, bool UNIT>
 cudaError_t launch_family(const Variant& v, const LagrangianParams& p, cudaStream_t stream, int max_blocks, bool* found);
+
+// Evaluation statistics on the staged pipelines (p.use_tma must be set); instantiated in ikl_stats_<layout>.cu.
+template <class C>
+cudaError_t launch_stats_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks) {
+  constexpr bool planes = C::LAYOUT == kPlanes;
+  auto* kernel = planes ? stats_planes_tma_kernel<C> : stats_rows_tma_kernel<C>;
+  constexpr size_t smem = planes ? TmaLayout<C>::kSmemBytes : RowsTmaLayout<C>::kSmemBytes;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    blocks_per_sm = n > 0 ? n : 1;
+  }
+  long long tiles = planes ? (p.batch + kTmaTile - 1) / kTmaTile : p.batch / kTmaTile;
+  if (tiles < 1) tiles = 1;
+  long long grid = (long long)grid_sms() * blocks_per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid > max_blocks) grid = max_blocks;
+  count_launch();
+  kernel<<<(unsigned)grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+template <int LAYOUT>
+cudaError_t launch_stats_family(const Variant& v, const LagrangianParams& p, cudaStream_t stream, int max_blocks, bool* found);
+
+// Argument checks, constants, layout detection and TMA descriptors shared by the entry points (ikl_api.cu).
+// Returns the layout (kStrided / kRows / kPlanes) and sets p.use_tma; a negative value is -IklStatus.
+int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const float* w_host, bool grad, float* dtheta, int64_t dt_sb,
+                              int64_t dt_sj, LagrangianParams& p, Variant& v);
 
 }  // namespace ikl

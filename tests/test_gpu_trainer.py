@@ -220,8 +220,9 @@ def test_device_dataset_matches_host_generator_statistically(cuda_device):
   assert abs(float(h.norm(dim=1).mean()) - float(d.norm(dim=1).mean())) < 0.02
 
 
-def test_eval_stats_match_per_sample_oracle(cuda_device):
-  from ikl import ConstraintSpec, synthetic
+def test_eval_stats_match_per_sample_oracle(cuda_device, monkeypatch):
+  from ikl import ConstraintSpec, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
   from ikl.device_data import eval_stats
   from oracle import ik_oracle as O
   for name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_1obs_static", "cfg_no_constraints"):
@@ -232,19 +233,27 @@ def test_eval_stats_match_per_sample_oracle(cuda_device):
     out = O.lagrangian(theta.double(), q_des.double(), torch.ones(spec.num_constraints).double(), ospec, obst.double(), per_sample=True)
     terms = out["per_sample_terms"]
     K = spec.num_constraints
-    counts, err = eval_stats(spec, theta.cuda(), q_des.cuda(), obst.cuda() if spec.dynamic else None)
-    counts = counts.cpu()
     want = (terms > 1e-4).sum(dim=0)
-    assert int((counts[:K] - want).abs().max()) <= 2, (counts[:K], want)        # fp32 vs fp64 right at the threshold
     names = O.constraint_names(ospec)
     jl = [i for i, n in enumerate(names) if "JL" in n]
     ob = [i for i, n in enumerate(names) if "OB" in n]
-    if jl:
-      assert abs(int(counts[16]) - int((terms[:, jl] > 0).any(dim=1).sum())) <= 2
-    if ob:
-      assert abs(int(counts[17]) - int((terms[:, ob] > 0).any(dim=1).sum())) <= 2
     want_err = torch.sqrt(out["position_err_sq"].sum(dim=1)).sum()
-    assert abs(float(err) - float(want_err)) <= 1e-5 * float(want_err)
+    th, qd, obd = theta.cuda(), q_des.cuda(), obst.cuda()
+    planes = synthetic.to_planes(th, qd, obd, max(spec.num_obstacles, 1))
+    big = torch.zeros(2 * len(theta), 3, device="cuda")
+    big[::2] = th
+    # the staged rows / planes pipelines (5000 = 9 full tiles + a ragged one) and the generic strided kernel
+    for args, kernel in (((th, qd, obd), "rows_tma"), (planes, "planes_tma"), ((big[::2], qd, obd), "strided")):
+      counts, err = eval_stats(spec, args[0], args[1], args[2] if spec.dynamic else None)
+      assert kernel in _cabi.last_kernel_name(), (_cabi.last_kernel_name(), kernel)
+      counts = counts.cpu()
+      assert int((counts[:K] - want).abs().max()) <= 2, (counts[:K], want)        # fp32 vs fp64 right at the threshold
+      assert int(counts[K:16].abs().max() if K < 16 else 0) == 0
+      if jl:
+        assert abs(int(counts[16]) - int((terms[:, jl] > 0).any(dim=1).sum())) <= 2
+      if ob:
+        assert abs(int(counts[17]) - int((terms[:, ob] > 0).any(dim=1).sum())) <= 2
+      assert abs(float(err) - float(want_err)) <= 1e-5 * float(want_err)
 
 
 def test_cuda_graph_train_step_matches_eager(tmp_path, cuda_device):
