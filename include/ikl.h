@@ -71,12 +71,16 @@ int32_t ikl_num_constraints(const IklSpec* spec);
  *   target   (B, >=2)      q_ee_desired; only x (c=0) and y (c=1) are read (trainer.py:192)
  *   obstacles(B, n_obs, 3+) per-sample circles (x, y, radius) for dynamic configs, else NULL
  * Native layouts (vectorised, no re-layout pass):
- *   "rows"   the reference's own tensors: theta (B,J) contiguous, target (B,3) contiguous,
- *            obstacles (B,4,4) contiguous [x, y, r, pad]   (kinematics/dataset.py:80-85,143-155)
+ *   "rows"   the reference's own tensors: theta (B,J) contiguous, target (B,3) or (B,2) contiguous,
+ *            obstacles (B,4,4) contiguous [x, y, r, pad]   (kinematics/dataset.py:80-85,143-155).
+ *            B >= 512 with 16-byte aligned tensors selects the bulk-copy staged kernel (whole
+ *            512-row tiles by cp.async.bulk); anything else the direct-load rows kernel.
  *   "planes" structure-of-arrays: every column its own contiguous plane of B floats (theta_sb == 1,
  *            theta_sj == plane pitch, ...).  Even B, 8-byte aligned planes and even pitches select the
  *            packed kernel; B % 4 == 0 with 16-byte aligned planes and pitches % 4 == 0 select the
- *            bulk-async (TMA) staged kernel, the fastest path.
+ *            TMA-staged kernel (tiled tensor-map loads), the fastest path.
+ * Environment switches for tests and measurements: IKL_FORCE_LAYOUT=strided|rows|planes,
+ * IKL_PLANES_TMA=0 and IKL_ROWS_TMA=0 (direct-load kernels instead of the staged ones).
  */
 typedef struct IklBatch {
   int64_t batch;                                   /* B >= 0 */

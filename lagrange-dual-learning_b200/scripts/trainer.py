@@ -190,7 +190,7 @@ class IkLagrangeDualTrainer(object):
     for key in inputs:
       inputs[key] = inputs[key].to(self.device, non_blocking=True)
     # device-resident data arrives as planes: evaluate the last layer transposed so theta is planes too and the
-    # bulk-async kernel applies; otherwise the reference's row-major tensors go through the rows kernel
+    # TMA-staged planes kernel applies; otherwise the reference's row-major tensors go through the rows kernel
     planes_in = inputs["q_ee_desired"].dim() == 2 and inputs["q_ee_desired"].shape[0] > 1 and inputs["q_ee_desired"].stride(0) == 1
     pred_joint_theta = self.model.forward_planes(inputs["input_tensor"]) if planes_in else self.model(inputs["input_tensor"])
     q_ee_desired = inputs["q_ee_desired"]
