@@ -1,19 +1,23 @@
 // ikl_lagrangian.cuh -- the fused FK + penalty + Lagrangian (+ analytic gradient) kernels.
 //
 // One persistent grid streams the batch once: per sample it reads theta, the target and the obstacle
-// rows, evaluates every constraint term (ikl_device.cuh), optionally writes d(sum_i w_i g_i)/d(theta),
-// and keeps K running sums per thread.  Sums go thread(fp32, short runs) -> thread(fp64) -> warp
-// shuffle -> block -> one fp64 partial per block per constraint -> the last block to finish adds the
-// partials in a fixed order, so results are bit-reproducible for a given launch geometry and no float
-// atomics are used.  (Reference: scripts/trainer.py:182-247 + :264 of miloknowles/lagrange-dual-learning.)
+// rows, evaluates every constraint term (ikl_packed.cuh / ikl_device.cuh), optionally writes
+// d(sum_i w_i g_i)/d(theta), and keeps K running sums per thread.  Sums go thread (fp32, <= 64 samples) ->
+// warp (fp32 butterfly) or thread (fp64 slot) -> fp64 per warp -> block -> one fp64 partial per block per
+// constraint -> the last block to finish adds the partials in a fixed order, so results are bit-reproducible
+// for a given launch geometry and no float atomics are used.
+// (Reference: scripts/trainer.py:182-247 + :264 of miloknowles/lagrange-dual-learning.)
 //
-// Memory layouts (see IklBatch in include/ikl.h):
-//   kStrided  any element strides, scalar loads, runtime link lengths        -- always-correct fallback
-//   kRows     the reference's own row-major tensors: theta (B,J), target (B,>=2), obstacles (B,4,4)
-//             read as one float4 per obstacle row; each thread evaluates the PAIR of samples (b, b + 256) with
-//             packed f32x2 maths (ikl_packed.cuh); the ragged tail runs the scalar per-sample code
-//   kPlanes   structure-of-arrays planes: each thread loads two consecutive samples of every plane with one
-//             8-byte access -- the loaded register pair IS the packed operand -- and stores d/dtheta the same way
+// Memory layouts (see IklBatch in include/ikl.h) and the kernels that serve them:
+//   kPlanes   structure-of-arrays planes.  lagrangian_planes_tma_kernel: tiled TMA loads (tensor maps) into a
+//             barrier-free shared-memory pipeline, thread v owns samples (2v, 2v+1) of a 512-sample tile; the staged
+//             register pair IS the packed f32x2 operand.  Fallback (odd alignment): direct 8-byte loads.
+//   kRows     the reference's own row-major tensors: theta (B,3), target (B,2|3), obstacles (B,4,4).
+//             lagrangian_rows_tma_kernel: three bulk copies per 512-row tile into the same pipeline, thread t owns
+//             samples (t, t + 256); ragged tail through the scalar code.  Fallback: one LDG.128 per obstacle row.
+//   kStrided  any element strides, 2 links, runtime link lengths -- scalar code, always correct.
+// The pipelines hand each pair of samples to a "body": LagrangianBody (sums + gradient) or StatsBody (the evaluation
+// statistics of scripts/evaluation/visualize_ik_solutions.py:97-119).
 #pragma once
 
 #include <type_traits>
