@@ -558,7 +558,7 @@ template <class C>
 struct TmaLayout {
   static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
   static constexpr int kHalfBytes = kPlanes * kTmaBoxBytes;
-  static constexpr int kStageBytes = 2 * kHalfBytes;
+  static constexpr int kStageBytes = (kTmaTile / kTmaBox) * kHalfBytes;
   static constexpr int kStages = IKL_TMA_STAGES;
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
 };
@@ -734,7 +734,7 @@ template <class C, class Body>
 __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars) {
   using L = TmaLayout<C>;
   constexpr int S = L::kStages;
-  static_assert(kThreads == kTmaBox, "thread v of a 512-sample tile owns samples (2v, 2v+1): half = v / 128");
+  static_assert(kTmaTile % kTmaBox == 0, "a tile is a whole number of 256-sample boxes; thread v owns samples (2v, 2v+1): box = v / 128");
   const long long B = p.batch;
   const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -757,7 +757,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
     const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
     mbar_expect_tx(bar, (unsigned)L::kStageBytes);    // boxes always deliver their full size (zero-filled past the batch end)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kTmaTile / kTmaBox; ++h) {
       const unsigned d = dst + h * L::kHalfBytes;
       const int x = b0 + h * kTmaBox;
       tma_load_2d(d, &p.tm_theta, x, 0, bar);
