@@ -508,549 +508,11 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
   sacc.flush(sacc1);
 }
 
-// ---- planes layout, TMA-staged ---------------------------------------------------------------------------------------
-// The planes of a batch are three tensors with the sample index innermost: theta {B, 3}, target {B, 2}, obstacles
-// {B, 3, n}.  A 512-sample tile is two 256-sample boxes (the hardware limit per box dimension) of each tensor: six tiled
-// TMA loads (SASS UTMALDG) land a whole tile of all 17 planes in one shared-memory stage and complete on the stage's
-// mbarrier.  Threads read their pair of samples with LDS.64 at immediate offsets and write d/dtheta straight to HBM.
-constexpr int kTmaTile = 2 * kThreads;                 // samples per tile
+}  // namespace ikl
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "IKL_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni IKL_DONE;\n"
-      "bra.uni IKL_WAIT;\n"
-      "IKL_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
-// are zero-filled by the hardware, so ragged last tiles need no special case.
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const TensorMap* tm, int x, int y, unsigned bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-               "l"(tm), "r"(x), "r"(y), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const TensorMap* tm, int x, int y, int z, unsigned bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
-constexpr int kTmaBox = 256;                           // samples per TMA box (the hardware limit per box dimension)
-constexpr int kTmaBoxBytes = kTmaBox * 4;
+#include "ikl_pipeline.cuh"      // staged kernels: run_planes_pipe / run_rows_pipe, LagrangianBody, StatsBody
 
-// Shared-memory budget: IKL_TMA_STAGES stages of [half (2)][plane][256 samples] + the mbarriers.  Measured on B200
-// (profiles/r01/kernel_table_pipeline.jsonl): 2 stages 0.2166 ms, 3 stages 0.2200 ms, 1 stage 0.2199 ms (fwd+bwd, 2^24).
-#ifndef IKL_TMA_STAGES
-#define IKL_TMA_STAGES 2
-#endif
-#ifndef IKL_PIPE_PROXY_FENCE
-#define IKL_PIPE_PROXY_FENCE 1
-#endif
-template <class C>
-struct TmaLayout {
-  static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
-  static constexpr int kHalfBytes = kPlanes * kTmaBoxBytes;
-  static constexpr int kStageBytes = (kTmaTile / kTmaBox) * kHalfBytes;
-  static constexpr int kStages = IKL_TMA_STAGES;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
-};
-
-// ---- what a pipeline does with a pair of samples ----------------------------------------------------------------------
-// The two staged pipelines (run_planes_pipe, run_rows_pipe) hand every pair of samples to a "body":
-//   pair(th, tx, ty, ob, bA, bB)   operands of samples bA and bB (packed: lo half = bA, hi half = bB)
-//   tile_done()                    once per tile, by every thread of the block (also by threads without a valid pair)
-//   finish()                       after the last tile
-// LagrangianBody: the K running sums (+ d/dtheta).  `r`: the rows pipeline keeps obstacle (k ^ r) in slot k.
-template <class C, class W2>
-struct LagrangianBody {
-  const LagrangianParams& p;
-  const W2& w2;
-  WarpSharedAcc<C::K>& sacc;
-  const int r;
-  f2 acc[C::K];
-  int since_flush;
-  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
-  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, WarpSharedAcc<C::K>& sa, int rr)
-      : p(pp), w2(w), sacc(sa), r(rr), since_flush(0) {
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  }
-  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
-    f2 dth[3], ee[3];
-    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
-    if (C::GRAD) {
-      if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
-#pragma unroll
-        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + bA, dth[j]);
-      } else {
-        float* dA = p.dtheta + bA * 3;
-        float* dB = p.dtheta + bB * 3;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          dA[j] = f2_lo(dth[j]);
-          dB[j] = f2_hi(dth[j]);
-        }
-      }
-    } else {
-      store_side_outputs(p, bA, bB, ee, tx, ty);
-    }
-  }
-  __device__ __forceinline__ void flush() {
-    if constexpr (kPermuted) sacc.template flush_xor4<kObstBase>(acc, r);
-    else sacc.flush(acc);
-  }
-  __device__ __forceinline__ void tile_done() {
-    if (++since_flush == kFlushSamples / 2) {
-      since_flush = 0;
-      flush();
-    }
-  }
-  __device__ __forceinline__ void finish() { flush(); }
-};
-
-// StatsBody: the evaluation statistics of scripts/evaluation/visualize_ik_solutions.py:97-119 (reference) -- per-constraint
-// counts of per-sample terms above a threshold, samples violating any joint limit / any obstacle (term > 0) and the
-// summed end-effector error sqrt(sum(position_err_sq)).  Same per-sample maths as the Lagrangian (eval_pair with fresh sums).
-constexpr int kStatSlots = kMaxK + 2;
-template <class C>
-struct StatsBody {
-  const LagrangianParams& p;
-  const int r;
-  unsigned cnt[C::K];
-  unsigned any_jl, any_ob;
-  double err;
-  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
-  __device__ __forceinline__ StatsBody(const LagrangianParams& pp, int rr) : p(pp), r(rr), any_jl(0), any_ob(0), err(0.0) {
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) cnt[i] = 0;
-  }
-  __device__ __forceinline__ void add(const float (&v)[C::K]) {
-    float mjl = -1.f, mob = -1.f;
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) {
-      cnt[i] += v[i] > p.stats_threshold;
-      if (C::JL && i >= 1 && i < 4) mjl = fmaxf(mjl, v[i]);
-      if (i >= kObstBase) mob = fmaxf(mob, v[i]);
-    }
-    any_jl += mjl > 0.f;
-    any_ob += mob > 0.f;
-    err += (double)__fsqrt_rn(v[0]);      // sqrt(position_err_sq.sum()) with position_err_sq = 0.5*e^2: the reference's |e|/sqrt(2)
-  }
-  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long, long long) {
-    f2 acc[C::K], dth[3], ee[3];
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-    const PackedHostWeights w2{p.pu};
-    eval_pair<C::NOBS, C::JL, false>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
-    float v[C::K];
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
-    add(v);
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) v[i] = f2_hi(acc[i]);
-    add(v);
-  }
-  __device__ __forceinline__ void tile_done() {}
-  // after the last tile: put the obstacle counters back in constraint order (rows pipeline), so that the caller can add
-  // tail samples in plain order before commit()
-  __device__ __forceinline__ void finish() {
-    if constexpr (kPermuted) {
-#pragma unroll
-      for (int bit = 1; bit <= 2; bit <<= 1) {
-        const bool sw = (r & bit) != 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k & bit) continue;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const unsigned a = cnt[kObstBase + 3 * k + j], b = cnt[kObstBase + 3 * (k | bit) + j];
-            cnt[kObstBase + 3 * k + j] = sw ? b : a;
-            cnt[kObstBase + 3 * (k | bit) + j] = sw ? a : b;
-          }
-        }
-      }
-    }
-  }
-  // warp sums -> the block's shared counters (s_counts zeroed by the caller before the pipeline's first barrier)
-  __device__ __forceinline__ void commit(unsigned* s_counts, double* s_err) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) {
-      const unsigned v = __reduce_add_sync(0xffffffffu, cnt[i]);
-      if (lane == 0 && v) atomicAdd(&s_counts[i], v);
-    }
-    const unsigned vj = __reduce_add_sync(0xffffffffu, any_jl), vo = __reduce_add_sync(0xffffffffu, any_ob);
-    double e = err;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-    if (lane == 0) {
-      if (vj) atomicAdd(&s_counts[kMaxK], vj);
-      if (vo) atomicAdd(&s_counts[kMaxK + 1], vo);
-      s_err[threadIdx.x >> 5] = e;
-    }
-  }
-};
-
-// block totals -> global (64-bit counters, fp64 error sum)
-__device__ __forceinline__ void stats_block_finalize(const LagrangianParams& p, const unsigned* s_counts, const double* s_err) {
-  __syncthreads();
-  if (threadIdx.x < kStatSlots && s_counts[threadIdx.x]) atomicAdd(p.stats_counts + threadIdx.x, (unsigned long long)s_counts[threadIdx.x]);
-  if (threadIdx.x == 0) {
-    double e = 0.0;
-#pragma unroll
-    for (int wq = 0; wq < kWarps; ++wq) e += s_err[wq];
-    atomicAdd(p.stats_pos_err, e);
-  }
-}
-
-// Arrive on an mbarrier (release: the caller's shared-memory reads are performed first) and report whether this was the
-// arrival that completed the phase: the returned state is the one BEFORE the arrival, so a pending count of 1 means "last".
-__device__ __forceinline__ bool mbar_arrive_is_last(unsigned bar) {
-  unsigned long long state;
-  unsigned pending;
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
-  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
-  return pending == 1u;
-}
-
-// Barrier-free pipeline.  A thread reads its operands from a stage at the START of a tile and then computes for ~450
-// instructions without touching shared memory, so the stage is handed back as soon as every warp has done its loads --
-// not a whole tile later, and without a block barrier.  Each warp arrives on the stage's "drained" mbarrier (count =
-// warps per block) after its loads; the warp whose arrival completes the phase re-arms the stage's "full" mbarrier and
-// issues the TMA loads of the tile that goes there next.  Nobody waits for anybody, only for data.  (Round-1 history,
-// profiles/r01/README.md: with 17 one-dimensional bulk copies per tile the issuing warp ran ~45 % more instructions than
-// its siblings and throttled the block whichever warp it was; six UTMALDG make the refill cheap enough to hand around.)
-template <class C, class Body>
-__device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars) {
-  using L = TmaLayout<C>;
-  constexpr int S = L::kStages;
-  static_assert(kTmaTile % kTmaBox == 0, "a tile is a whole number of 256-sample boxes; thread v owns samples (2v, 2v+1): box = v / 128");
-  const long long B = p.batch;
-  const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
-  const unsigned drained0 = bar0 + 8 * S;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bar0 + 8 * s, 1);
-      mbar_init(drained0 + 8 * s, kWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // Stage layout: [half (2)][plane][256 samples]; each half is what one box of every group delivers.
-  auto issue = [&](long long tile, int stage) {      // one thread
-    const int b0 = (int)(tile * kTmaTile);
-    const unsigned bar = bar0 + 8 * stage;
-    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
-    mbar_expect_tx(bar, (unsigned)L::kStageBytes);    // boxes always deliver their full size (zero-filled past the batch end)
-#pragma unroll
-    for (int h = 0; h < kTmaTile / kTmaBox; ++h) {
-      const unsigned d = dst + h * L::kHalfBytes;
-      const int x = b0 + h * kTmaBox;
-      tma_load_2d(d, &p.tm_theta, x, 0, bar);
-      tma_load_2d(d + 3 * kTmaBoxBytes, &p.tm_target, x, 0, bar);
-      if (C::DYN) tma_load_3d(d + 5 * kTmaBoxBytes, &p.tm_obst, x, 0, 0, bar);
-    }
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (t < ntiles) issue(t, s);
-    }
-  }
-
-  int stage = 0;
-  unsigned parity = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar0 + 8 * stage, parity);
-    const long long b = tile * kTmaTile + 2 * tid;
-    const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
-    f2 th[3], ob[C::NOB][3];
-    int pl = 0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
-    const f2 tx = *reinterpret_cast<const f2*>(base + 3 * kTmaBoxBytes);
-    const f2 ty = *reinterpret_cast<const f2*>(base + 4 * kTmaBoxBytes);
-    pl = 5;
-    if (C::DYN) {
-#pragma unroll
-      for (int k = 0; k < C::NOBS; ++k) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c, ++pl) ob[k][c] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
-      }
-    } else {
-      static_obstacles_packed<C>(p, ob);
-    }
-    // hand the stage back: the last of the block's warps to get here refills it
-    __syncwarp();
-    if (lane == 0) {
-      const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
-      const long long next = tile + (long long)S * gridDim.x;
-      if (last && next < ntiles) {
-#if IKL_PIPE_PROXY_FENCE
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-        issue(next, stage);
-      }
-    }
-    __syncwarp();
-    if (b < B) body.pair(th, tx, ty, ob, b, b + 1);
-    body.tile_done();
-    if (++stage == S) {
-      stage = 0;
-      parity ^= 1u;
-    }
-  }
-  body.finish();
-}
-
-template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  using L = TmaLayout<C>;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
-  __shared__ float2 s_lam2[kMaxK];
-  __shared__ double s_warp[kWarps][kMaxK];
-  if constexpr (C::MODE == kGradDevW) {
-    if (threadIdx.x < C::K) {
-      const float l = __ldg(p.w_dev + threadIdx.x);
-      s_lam2[threadIdx.x] = make_float2(l, l);
-    }
-  }
-  WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
-  auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, 0);
-    run_planes_pipe<C>(p, body, dyn_smem, bars);
-  };
-  if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
-  else run(PackedHostWeights{p.pu});
-  block_finalize<C::K>(p, s_warp);
-}
-
-// ---- rows layout, bulk-copy staged -------------------------------------------------------------------------------------
-// The reference's own tensors are contiguous per tile: 512 rows of theta (6 KiB), of q_ee_desired (4 or 6 KiB) and of
-// dynamic_obstacles (32 KiB) -- three one-dimensional bulk copies (SASS UBLKCP) per tile into the same barrier-free
-// pipeline as the planes kernel.  Thread t owns samples (t, t + 256) of the tile, like the direct-load rows kernel.
-// Shared-memory reads: theta / target rows are 3 (2) words apart -- conflict-free; an obstacle row is 16 words and a
-// sample 64 words, so the four LDS.128 of a sample are issued in the order k ^ r, r = (t >> 1) & 3, which spreads the
-// eight lanes of a quarter-warp over all 32 banks.  The thread therefore holds obstacle (k ^ r) in slot k; the maths is
-// symmetric in the obstacles except for the multiplier and the sum each term belongs to: multipliers come from a
-// per-r permuted table in shared memory, sums are put back in order when they are flushed (WarpSharedAcc::flush_xor4).
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar) : "memory");
-}
-
-template <class C>
-struct RowsTmaLayout {
-  static constexpr bool kSupported = C::J == 3 && (!C::DYN || C::NOBS == kMaxObst);
-  static constexpr int kThetaBytes = kTmaTile * 3 * 4;
-  static constexpr int kTargetBytes = kTmaTile * 3 * 4;                 // room for target rows of 2 or 3 floats
-  static constexpr int kObstBytes = C::DYN ? kTmaTile * 4 * kMaxObst * 4 : 0;
-  static constexpr int kStageBytes = kThetaBytes + kTargetBytes + kObstBytes;
-  static constexpr int kStages = IKL_TMA_STAGES;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);                  // index of the first obstacle constraint
-};
-
-template <class C, class Body>
-__device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars, int r) {
-  using L = RowsTmaLayout<C>;
-  constexpr int S = L::kStages;
-  const long long ntiles = p.batch / kTmaTile;       // full tiles only; the caller evaluates the ragged tail
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int tg_sb = (int)p.tg_sb;                    // 2 or 3 (checked on the host)
-  const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
-  const unsigned drained0 = bar0 + 8 * S;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bar0 + 8 * s, 1);
-      mbar_init(drained0 + 8 * s, kWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  auto issue = [&](long long tile, int stage) {      // one thread
-    const long long b0 = tile * kTmaTile;
-    const unsigned bar = bar0 + 8 * stage;
-    const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
-    const unsigned tg_bytes = (unsigned)(kTmaTile * 4) * (unsigned)tg_sb;
-    mbar_expect_tx(bar, L::kThetaBytes + tg_bytes + L::kObstBytes);
-    bulk_g2s(dst, p.theta + b0 * 3, L::kThetaBytes, bar);
-    bulk_g2s(dst + L::kThetaBytes, p.target + b0 * tg_sb, tg_bytes, bar);
-    if (C::DYN) bulk_g2s(dst + L::kThetaBytes + L::kTargetBytes, p.obst + b0 * (4 * kMaxObst), L::kObstBytes, bar);
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (t < ntiles) issue(t, s);
-    }
-  }
-
-  int stage = 0;
-  unsigned parity = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar0 + 8 * stage, parity);
-    const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
-    f2 th[3], ob[C::NOB][3];
-    const float* tA = reinterpret_cast<const float*>(st) + 3 * tid;
-    const float* tB = tA + 3 * kThreads;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) th[j] = f2_make(tA[j], tB[j]);
-    const float* gA = reinterpret_cast<const float*>(st + L::kThetaBytes) + tg_sb * tid;
-    const float* gB = gA + tg_sb * kThreads;
-    const f2 tx = f2_make(gA[0], gB[0]);
-    const f2 ty = f2_make(gA[1], gB[1]);
-    if constexpr (C::DYN) {
-      const float4* oA = reinterpret_cast<const float4*>(st + L::kThetaBytes + L::kTargetBytes) + kMaxObst * tid;
-      const float4* oB = oA + kMaxObst * kThreads;
-#pragma unroll
-      for (int k = 0; k < C::NOBS; ++k) {
-        const float4 a = oA[k ^ r], b4 = oB[k ^ r];
-        ob[k][0] = f2_make(a.x, b4.x);
-        ob[k][1] = f2_make(a.y, b4.y);
-        ob[k][2] = f2_make(a.z, b4.z);
-      }
-    } else {
-      static_obstacles_packed<C>(p, ob);
-    }
-    // hand the stage back: the last of the block's warps to get here refills it
-    __syncwarp();
-    if (lane == 0) {
-      const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
-      const long long next = tile + (long long)S * gridDim.x;
-      if (last && next < ntiles) {
-#if IKL_PIPE_PROXY_FENCE
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-        issue(next, stage);
-      }
-    }
-    __syncwarp();
-    const long long bA = tile * kTmaTile + tid;
-    body.pair(th, tx, ty, ob, bA, bA + kThreads);
-    body.tile_done();
-    if (++stage == S) {
-      stage = 0;
-      parity ^= 1u;
-    }
-  }
-  body.finish();
-}
-
-template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  using L = RowsTmaLayout<C>;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
-  __shared__ float2 s_lam_perm[4][kMaxK];      // multipliers as (w, w) pairs, obstacle entries permuted by k ^ r
-  __shared__ double s_warp[kWarps][kMaxK];
-  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
-  constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::MODE == kGradDevW);
-  if constexpr (kSmemWeights) {
-    if (threadIdx.x < 4 * kMaxK) {
-      const int rr = threadIdx.x / kMaxK, i = threadIdx.x % kMaxK;
-      int src = i;
-      if (C::DYN && i >= L::kObstBase && i < C::K) {
-        const int q = i - L::kObstBase, k = q / 3, j = q % 3;
-        src = L::kObstBase + 3 * (k ^ rr) + j;
-      }
-      float l = 0.f;
-      if (i < C::K) l = (C::MODE == kGradDevW) ? __ldg(p.w_dev + src) : p.u.w[src];
-      s_lam_perm[rr][i] = make_float2(l, l);
-    }
-  }
-  WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
-  auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, r);
-    run_rows_pipe<C>(p, body, dyn_smem, bars, r);
-  };
-  if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]});
-  else run(PackedHostWeights{p.pu});
-  // ragged tail (< 512 samples), one sample per thread through the scalar code
-  {
-    const long long full = (p.batch / kTmaTile) * kTmaTile;
-    float sacc1[C::K];
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) sacc1[i] = 0.f;
-    auto tail = [&](const auto& w) {
-      for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
-        float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3];
-        if (!C::DYN) static_obstacles<C>(p, ob);
-        load_sample<C>(p, b, th, tx, ty, ob);
-        eval_sample<3, C::NOBS, C::JL, C::GRAD, true>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
-        store_sample<C>(p, b, dth, ee, tx, ty);
-      }
-    };
-    if (full < p.batch) {
-      if constexpr (C::MODE == kGradDevW) tail(DeviceWeights<C::K>(p.u, p.w_dev));
-      else tail(HostWeights(p.u, nullptr));
-    }
-    sacc.flush(sacc1);
-  }
-  block_finalize<C::K>(p, s_warp);
-}
-
-// ---- evaluation statistics through the same pipelines -------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) stats_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  using L = TmaLayout<C>;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
-  __shared__ unsigned s_counts[kStatSlots];
-  __shared__ double s_err[kWarps];
-  if (threadIdx.x < kStatSlots) s_counts[threadIdx.x] = 0;      // ordered by the pipeline's first block barrier
-  StatsBody<C> body(p, 0);
-  run_planes_pipe<C>(p, body, dyn_smem, bars);
-  body.commit(s_counts, s_err);
-  stats_block_finalize(p, s_counts, s_err);
-}
-
-template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) stats_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  using L = RowsTmaLayout<C>;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
-  __shared__ unsigned s_counts[kStatSlots];
-  __shared__ double s_err[kWarps];
-  if (threadIdx.x < kStatSlots) s_counts[threadIdx.x] = 0;
-  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
-  StatsBody<C> body(p, r);
-  run_rows_pipe<C>(p, body, dyn_smem, bars, r);
-  // ragged tail (< 512 rows), one sample per thread through the scalar code
-  const long long full = (p.batch / kTmaTile) * kTmaTile;
-  const HostWeights w(p.u, nullptr);
-  for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
-    float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3], acc[C::K];
-    if (!C::DYN) static_obstacles<C>(p, ob);
-    load_sample<C>(p, b, th, tx, ty, ob);
-#pragma unroll
-    for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
-    eval_sample<3, C::NOBS, C::JL, false, true>(p.u, w, th, tx, ty, ob, acc, dth, ee);
-    body.add(acc);
-  }
-  body.commit(s_counts, s_err);
-  stats_block_finalize(p, s_counts, s_err);
-}
+namespace ikl {
 
 template <class C>
 __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_kernel(const __grid_constant__ LagrangianParams p) {
