@@ -439,6 +439,43 @@ def test_rows_bulk_copy_pipeline(B, cuda_device, monkeypatch):
   assert float((v_a - v_b).abs().max()) <= 2e-6 * float(v_a.abs().max())
 
 
+@pytest.mark.parametrize("layout", ["planes", "rows"])
+def test_staged_kernels_replay_in_a_cuda_graph(layout, cuda_device, monkeypatch):
+  """The staged kernels carry TMA descriptors / pointers in their parameter block: captured once, replayed on new data
+  written into the same buffers, they must give what an eager launch gives (device-side multipliers, so lambda can change too)."""
+  from ikl import fused, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  dev = cuda_device
+  B = 2048 + 512
+  spec, _ = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  def batch(seed):
+    th, qd, ob = synthetic.make_batch(B, seed=seed, device="cuda:0")
+    return synthetic.to_planes(th, qd, ob) if layout == "planes" else (th, qd, ob)
+  th, qd, ob = batch(1)
+  lam = torch.linspace(0.5, 2.0, 16, device=dev)
+  dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    fused.lagrangian_forward_backward(spec, th, qd, ob, lam, dtheta=dth)      # warm-up outside the capture
+  torch.cuda.current_stream().wait_stream(side)
+  torch.cuda.synchronize()
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    viol, loss, _ = fused.lagrangian_forward_backward(spec, th, qd, ob, lam, dtheta=dth)
+  assert ("<%s_tma," % layout) in _cabi.last_kernel_name()
+  for seed in (2, 3):
+    th2, qd2, ob2 = batch(seed)
+    for dst, src in ((th, th2), (qd, qd2), (ob, ob2)):
+      dst.copy_(src)
+    lam.mul_(1.25)
+    g.replay()
+    torch.cuda.synchronize()
+    got = (viol.clone(), float(loss), dth.clone())
+    v_e, l_e, d_e = fused.lagrangian_forward_backward(spec, th2, qd2, ob2, lam.clone())
+    assert torch.equal(got[0], v_e) and got[1] == float(l_e) and torch.equal(got[2], d_e)
+
+
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
   """theta exactly at a limit / at mid-range, a tip exactly on a circle, a tip exactly on a centre."""
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
