@@ -123,10 +123,11 @@ def measure_callers(args):
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   for cfg_name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static"):
     cfg = standard_config(cfg_name)
-    device_data.generate_dataset(cfg, B, seed=1, device="cuda:0")
+    d = device_data.generate_dataset(cfg, B, seed=1, device="cuda:0")
     torch.cuda.synchronize()
     ev0.record()
     for rep in range(3):
+      del d                                   # hand the output blocks back to the caching allocator: no cudaMalloc in the timed region
       d = device_data.generate_dataset(cfg, B, seed=2 + rep, device="cuda:0")
     ev1.record()
     torch.cuda.synchronize()
