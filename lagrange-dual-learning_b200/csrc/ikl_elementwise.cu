@@ -32,20 +32,33 @@ inline unsigned ew_grid_unrolled(long long n) { return ew_grid((n + kEwUnroll - 
 
 // kinematics/forward_kinematics.py:64-81 -- tips_out block k = tip J-k (end effector first), rows (x, y, angle)
 template <int J>
+__device__ __forceinline__ void fk_sample(const float (&th)[J], const Lengths& L, float (&out)[J][3]) {
+  float phi = 0.f, x = 0.f, y = 0.f;
+#pragma unroll
+  for (int m = 0; m < J; ++m) {
+    phi = (m == 0) ? th[0] : __fadd_rn(phi, th[m]);
+    float s, c;
+    sincosf(phi, &s, &c);
+    x = (m == 0) ? __fmul_rn(L.v[0], c) : __fadd_rn(x, __fmul_rn(L.v[m], c));
+    y = (m == 0) ? __fmul_rn(L.v[0], s) : __fadd_rn(y, __fmul_rn(L.v[m], s));
+    out[J - 1 - m][0] = x;
+    out[J - 1 - m][1] = y;
+    out[J - 1 - m][2] = phi;
+  }
+}
+
+template <int J>
 __global__ void __launch_bounds__(kEwThreads) fk_forward_kernel(const float* __restrict__ theta, long long sb, long long sj, long long B,
                                                                Lengths L, float* __restrict__ tips) {
   for (long long b = (long long)blockIdx.x * kEwThreads + threadIdx.x; b < B; b += (long long)gridDim.x * kEwThreads) {
-    float phi = 0.f, x = 0.f, y = 0.f;
+    float th[J], out[J][3];
 #pragma unroll
-    for (int m = 0; m < J; ++m) {
-      const float t = theta[b * sb + m * sj];
-      phi = (m == 0) ? t : __fadd_rn(phi, t);
-      float s, c;
-      sincosf(phi, &s, &c);
-      x = (m == 0) ? __fmul_rn(L.v[0], c) : __fadd_rn(x, __fmul_rn(L.v[m], c));
-      y = (m == 0) ? __fmul_rn(L.v[0], s) : __fadd_rn(y, __fmul_rn(L.v[m], s));
-      float* o = tips + ((long long)(J - 1 - m) * B + b) * 3;
-      o[0] = x; o[1] = y; o[2] = phi;
+    for (int m = 0; m < J; ++m) th[m] = theta[b * sb + m * sj];
+    fk_sample<J>(th, L, out);
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      float* o = tips + ((long long)k * B + b) * 3;
+      o[0] = out[k][0]; o[1] = out[k][1]; o[2] = out[k][2];
     }
   }
 }

@@ -87,13 +87,15 @@ def measure_elementwise(args):
   except Exception:
     pass
   lim = torch.tensor([-2.094395, 2.094395], device="cuda:0").unsqueeze(0).expand(B, -1)
+  # (name, algorithmic bytes per sample, bytes per sample in the 32-byte sectors the strided views touch, call)
   cases = [
-      ("fk_forward (12 B in, 36 B out per sample)", 48, lambda: ops.fk_forward_kinematics(theta)),
-      ("circle_penalty on column views (16 B in effective sectors ~ 5 x 4 B, 4 B out)", 24,
+      ("fk_forward (12 B in, 36 B out per sample)", 48, 48, lambda: ops.fk_forward_kinematics(theta)),
+      ("circle_penalty on column views of (B,3) and (B,4,4) tensors (5 x 4 B in, 4 B out)", 24, 12 + 32 + 4,
        lambda: ops.circle_penalty(q_des[:, 0], q_des[:, 1], obst[:, 0, 0], obst[:, 0, 1], obst[:, 0, 2], 1.0, 0.005)),
-      ("joint_limit_penalty on a column view (4 B in, 4 B out)", 8, lambda: ops.joint_limit_penalty(theta[:, 1], lim[:, 0], lim[:, 1], 0.005, 1.0)),
+      ("joint_limit_penalty on a column view of (B,3) (4 B in, 4 B out)", 8, 12 + 4,
+       lambda: ops.joint_limit_penalty(theta[:, 1], lim[:, 0], lim[:, 1], 0.005, 1.0)),
   ]
-  for name, nbytes, fn in cases:
+  for name, nbytes, sector_bytes, fn in cases:
     for _ in range(3):
       fn()
     torch.cuda.synchronize()
@@ -107,7 +109,9 @@ def measure_elementwise(args):
     print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "kernel": name, "ms_mean": round(ms, 4),
                       "gsamples_per_s": round(B / ms / 1e6, 2), "algo_GBps": round(nbytes * B / ms / 1e6, 1),
                       "frac_of_hbm_peak": round(nbytes * B / ms / 1e6 / peak, 4),
-                      "note": "includes the torch allocation of the output; strided column views read whole sectors"}), flush=True)
+                      "sector_GBps": round(sector_bytes * B / ms / 1e6, 1),
+                      "frac_of_hbm_peak_on_sector_bytes": round(sector_bytes * B / ms / 1e6 / peak, 4),
+                      "note": "includes the torch allocation of the output; strided column views move whole 32-byte sectors"}), flush=True)
 
 
 def measure_callers(args):
