@@ -19,16 +19,35 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+// Wait for a phase of an mbarrier.  The common case is one successful poll; the spinning path is a separate (non-inlined)
+// function so its poll counter costs the hot loop no register.  A copy that never completes (a transaction-count mismatch
+// would do it) must not hang the GPU: after 2^26 unsuccessful polls (each try_wait suspends for a hardware time slice;
+// seconds in total, against microseconds for a copy) the kernel traps and the launch reports an error instead.
+static __device__ __noinline__ void mbar_wait_spin(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
       "IKL_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra.uni IKL_DONE;\n"
-      "bra.uni IKL_WAIT;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 0x4000000;\n"
+      "@p bra.uni IKL_WAIT;\n"
+      "trap;\n"
       "IKL_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (!done) mbar_wait_spin(bar, parity);
 }
 // Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
 // are zero-filled by the hardware, so ragged last tiles need no special case.
