@@ -559,20 +559,38 @@ inline int grid_sms() {
   return n > 0 ? n : 1;
 }
 
+// Resident blocks per SM of a kernel with `smem` bytes of dynamic shared memory, cached per (kernel instantiation, device):
+// the opt-in to more than 48 KiB of dynamic shared memory is a per-device function attribute, so a process that drives
+// several GPUs must set it on each of them.
+template <class Kernel>
+cudaError_t resident_blocks(Kernel kernel, size_t smem, int (&cache)[64], int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (cache[slot] == 0 || slot != dev) {
+    if (smem > 0) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    cache[slot] = n > 0 ? n : 1;
+  }
+  *out = cache[slot];
+  return cudaSuccess;
+}
+
 template <class C>
 cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks, const char* name) {
   if constexpr (C::LAYOUT == kPlanes) {
     if (p.use_tma) {
-      static int tma_blocks_per_sm = 0;
+      static int cache[64] = {0};
       constexpr size_t smem = TmaLayout<C>::kSmemBytes;
-      if (tma_blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(lagrangian_planes_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_planes_tma_kernel<C>, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        tma_blocks_per_sm = n > 0 ? n : 1;
-      }
+      int tma_blocks_per_sm = 1;
+      const cudaError_t e = resident_blocks(lagrangian_planes_tma_kernel<C>, smem, cache, &tma_blocks_per_sm);
+      if (e != cudaSuccess) return e;
       long long tiles = (p.batch + kTmaTile - 1) / kTmaTile;
       if (tiles < 1) tiles = 1;
       long long grid = (long long)grid_sms() * tma_blocks_per_sm;
@@ -586,16 +604,11 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
   }
   if constexpr (C::LAYOUT == kRows && RowsTmaLayout<C>::kSupported) {
     if (p.use_tma) {
-      static int rows_blocks_per_sm = 0;
+      static int cache[64] = {0};
       constexpr size_t smem = RowsTmaLayout<C>::kSmemBytes;
-      if (rows_blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(lagrangian_rows_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_rows_tma_kernel<C>, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        rows_blocks_per_sm = n > 0 ? n : 1;
-      }
+      int rows_blocks_per_sm = 1;
+      const cudaError_t e = resident_blocks(lagrangian_rows_tma_kernel<C>, smem, cache, &rows_blocks_per_sm);
+      if (e != cudaSuccess) return e;
       long long tiles = p.batch / kTmaTile;
       if (tiles < 1) tiles = 1;
       long long grid = (long long)grid_sms() * rows_blocks_per_sm;
@@ -607,12 +620,11 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       return cudaGetLastError();
     }
   }
-  static int blocks_per_sm = 0;      // per instantiation; same answer on every device of a homogeneous node
-  if (blocks_per_sm == 0) {
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lagrangian_kernel<C>, kThreads, 0);
+  static int cache[64] = {0};
+  int blocks_per_sm = 1;
+  {
+    const cudaError_t e = resident_blocks(lagrangian_kernel<C>, 0, cache, &blocks_per_sm);
     if (e != cudaSuccess) return e;
-    blocks_per_sm = n > 0 ? n : 1;
   }
   const long long per_block = (long long)kThreads * (C::LAYOUT == kStrided ? IKL_ROWS_UNROLL : 2);
   long long tiles = (p.batch + per_block - 1) / per_block;
@@ -643,14 +655,11 @@ cudaError_t launch_stats_cfg(const LagrangianParams& p, cudaStream_t stream, int
   constexpr bool planes = C::LAYOUT == kPlanes;
   auto* kernel = planes ? stats_planes_tma_kernel<C> : stats_rows_tma_kernel<C>;
   constexpr size_t smem = planes ? TmaLayout<C>::kSmemBytes : RowsTmaLayout<C>::kSmemBytes;
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int cache[64] = {0};
+  int blocks_per_sm = 1;
+  {
+    const cudaError_t e = resident_blocks(kernel, smem, cache, &blocks_per_sm);
     if (e != cudaSuccess) return e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    blocks_per_sm = n > 0 ? n : 1;
   }
   long long tiles = planes ? (p.batch + kTmaTile - 1) / kTmaTile : p.batch / kTmaTile;
   if (tiles < 1) tiles = 1;

@@ -61,3 +61,29 @@ def test_two_gpu_trainer_matches_single_process_reference(tmp_path):
   s.close()
   mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
   assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_driving_two_devices():
+  """The staged kernels opt in to > 48 KiB of dynamic shared memory, a per-device function attribute: one process that
+  launches them on cuda:0 and then on cuda:1 must get the same numbers on both (and no launch error on the second)."""
+  from ikl import ConstraintSpec, fused, synthetic, _cabi
+  from ikl.device_data import eval_stats
+  spec = ConstraintSpec.from_config(config_json(NAME), 3, 0.005, 1.0)
+  B = 4096
+  theta, q_des, obst = synthetic.make_batch(B, seed=3)
+  lam = [0.5 + 0.1 * i for i in range(16)]
+  results = []
+  for d in (0, 1):
+    dev = torch.device("cuda", d)
+    th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+    out = []
+    for args in ((th, qd, ob), synthetic.to_planes(th, qd, ob)):
+      v, l, g = fused.lagrangian_forward_backward(spec, *args, lam)
+      assert "_tma," in _cabi.last_kernel_name()
+      counts, err = eval_stats(spec, *args)
+      torch.cuda.synchronize(dev)
+      out += [v.cpu(), g.contiguous().cpu(), counts.cpu(), err.cpu()]
+    results.append(out)
+  for a, b in zip(*results):
+    assert torch.equal(a, b)
