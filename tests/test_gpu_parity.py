@@ -476,6 +476,56 @@ def test_staged_kernels_replay_in_a_cuda_graph(layout, cuda_device, monkeypatch)
     assert torch.equal(got[0], v_e) and got[1] == float(l_e) and torch.equal(got[2], d_e)
 
 
+def _random_config(rng):
+  """A constraint JSON in the reference's format with random content: 0-4 static or dynamic circles, joint limits on/off."""
+  dyn = bool(rng.integers(0, 2))
+  n = int(rng.integers(0, 5))
+  lim = float(rng.uniform(0.8, 3.0))
+  static = [] if dyn else [{"type": "circle", "radius": float(rng.uniform(0.15, 0.7)), "x": float(rng.uniform(-2, 2)),
+                            "y": float(rng.uniform(-2, 2))} for _ in range(n)]
+  return {"static_constraints": {"joint_limits": [-lim * float(rng.uniform(0.5, 1.0)), lim], "obstacles": static},
+          "dynamic_constraints": {"random_obstacles": dyn, "random_obstacles_num": n if dyn else 0,
+                                  "random_obstacles_template": {"type": "circle", "radius": 0.4, "x": 1.0, "y": 1.0}},
+          "enforce_joint_limits": bool(rng.integers(0, 4) > 0), "enforce_obstacles": n > 0}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_every_layout(seed, cuda_device, monkeypatch):
+  """Randomised specs (number / kind of obstacles, limits, slopes in either order or equal, per-sample radii), batch sizes
+  on both sides of the staged kernels' thresholds, every layout, host and device multipliers -- against the fp64 oracle."""
+  from ikl import ConstraintSpec, synthetic
+  rng = np.random.default_rng(900 + seed)
+  cfg = _random_config(rng)
+  good, bad = (float(rng.uniform(0.0, 1.5)), float(rng.uniform(0.0, 1.5)))
+  if seed % 5 == 0:
+    bad = good                                            # equal slopes: the penalty is linear, no kink at all
+  spec = ConstraintSpec.from_config(cfg, 3, good, bad)
+  ospec = O.spec_from_json(cfg, 3, good, bad)
+  K = spec.num_constraints
+  assert K == ospec.num_constraints
+  B = int(rng.choice([6, 64, 508, 512, 1536, 2052, 70000]))
+  theta, q_des, obst = synthetic.make_batch(B, seed=int(rng.integers(1 << 30)))
+  obst[:, :, 2] = torch.from_numpy(rng.uniform(0.1, 0.8, size=(B, 4)).astype(np.float32))     # per-sample radii
+  lam = rng.uniform(0.0, 3.0, size=K).astype(np.float32)
+  lam[rng.integers(0, K)] = 0.0
+  sums64, abs_sums, dth64, kink, truth = oracle_truth(ospec, theta, q_des, obst, lam)
+  ref_v = None
+  for layout in LAYOUTS:
+    if layout == "planes" and B % 2:
+      continue
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(cuda_device)):
+      viol, loss, dth, kname = run_layout(layout, spec, theta, q_des, obst, weights, True, monkeypatch)
+      assert layout in kname or "<strided," in kname, (kname, layout)     # combinations without a fast instantiation fall back
+      assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums + 1e-30), (kname, cfg)
+      close(loss, float((lam.astype(np.float64) * sums64).sum()), scale=float((lam * abs_sums).sum()) + 1e-30)
+      grad_close(dth, dth64, truth)
+      if ref_v is None:
+        ref_v = viol
+      assert np.all(np.abs(viol - ref_v) <= 4e-6 * abs_sums + 1e-30)
+    viol_f, _, _, kname = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
+    assert np.array_equal(viol_f, viol), kname
+
+
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
   """theta exactly at a limit / at mid-range, a tip exactly on a circle, a tip exactly on a centre."""
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
