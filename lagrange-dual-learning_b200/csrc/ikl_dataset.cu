@@ -294,6 +294,14 @@ IklStatus ikl_eval_stats(const IklSpec* spec, const IklBatch* in, float threshol
   IKL_STATS_CASE(2, true, true)
   IKL_STATS_CASE(3, true, true)
   IKL_STATS_CASE(4, true, true)
+  IKL_STATS_CASE(1, false, false)
+  IKL_STATS_CASE(2, false, false)
+  IKL_STATS_CASE(3, false, false)
+  IKL_STATS_CASE(4, false, false)
+  IKL_STATS_CASE(1, true, false)
+  IKL_STATS_CASE(2, true, false)
+  IKL_STATS_CASE(3, true, false)
+  IKL_STATS_CASE(4, true, false)
 #undef IKL_STATS_CASE
   return IKL_ERR_UNSUPPORTED;
 }

@@ -1,5 +1,5 @@
 // ikl_stats_family.inl -- included by ikl_stats_<layout>.cu after defining IKL_FAMILY_LAYOUT: the evaluation-statistics
-// kernels for the combinations the five task configs and their dynamic siblings use.
+// kernels for every (obstacle count, static / dynamic, joint limits on / off) combination.
 #include "ikl_lagrangian.cuh"
 
 namespace ikl {
@@ -22,6 +22,16 @@ cudaError_t launch_stats_family<IKL_FAMILY_LAYOUT>(const Variant& v, const Lagra
   IKL_CASE(2, true, true)
   IKL_CASE(3, true, true)
   IKL_CASE(4, true, true)
+  IKL_CASE(2, false, true)
+  IKL_CASE(3, false, true)
+  IKL_CASE(1, false, false)
+  IKL_CASE(2, false, false)
+  IKL_CASE(3, false, false)
+  IKL_CASE(4, false, false)
+  IKL_CASE(1, true, false)
+  IKL_CASE(2, true, false)
+  IKL_CASE(3, true, false)
+  IKL_CASE(4, true, false)
 #undef IKL_CASE
   *found = false;
   return cudaSuccess;

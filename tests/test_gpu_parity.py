@@ -524,6 +524,24 @@ def test_random_configurations_every_layout(seed, cuda_device, monkeypatch):
       assert np.all(np.abs(viol - ref_v) <= 4e-6 * abs_sums + 1e-30)
     viol_f, _, _, kname = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
     assert np.array_equal(viol_f, viol), kname
+  # evaluation statistics of the same batch on the staged pipelines (rows, planes) and the generic kernel
+  from ikl.device_data import eval_stats
+  from ikl import _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  terms = O.lagrangian(theta.double(), q_des.double(), torch.ones(K).double(), ospec, obst.double() if ospec.dynamic else None,
+                       per_sample=True)["per_sample_terms"]
+  want = (terms > 1e-4).sum(dim=0)
+  slack = max(2, B // 4000)                                # fp32 vs fp64 right at the threshold
+  dev = cuda_device
+  th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+  arg_sets = [(th, qd, ob)]
+  if B % 2 == 0:
+    arg_sets.append(synthetic.to_planes(th, qd, ob, max(spec.num_obstacles, 1)))
+  for args in arg_sets:
+    counts, err = eval_stats(spec, args[0], args[1], args[2] if spec.dynamic else None)
+    assert int((counts[:K].cpu() - want).abs().max()) <= slack, (_cabi.last_kernel_name(), counts[:K].cpu(), want)
+    want_err = float(torch.sqrt(terms[:, 0]).sum())
+    assert abs(float(err) - want_err) <= 1e-5 * want_err
 
 
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
