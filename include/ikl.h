@@ -140,7 +140,8 @@ IklStatus ikl_dual_update(const float* lam_in, const double* viol_sum, const flo
 
 /* ---- function-level drop-ins (let an unchanged scripts/trainer.py reach CUDA op by op) ---------- */
 
-/* kinematics/forward_kinematics.py:47-83 ForwardKinematicsThreeLinkTorch (and the 2-link maths of :7-22).
+/* kinematics/forward_kinematics.py:47-83 ForwardKinematicsThreeLinkTorch (num_links 3; also 2: the maths of :7-22, and
+ * 8: what the reference's non-running eight-link function :86-110 spells out).
  * tips_out: J contiguous (B,3) blocks, END EFFECTOR FIRST: block k holds tip J-k as (x, y, cumulative angle). */
 IklStatus ikl_fk_forward(const float* theta, int64_t theta_sb, int64_t theta_sj, int64_t batch,
                          int32_t num_links, const float* link_length_host, float* tips_out, void* stream);

@@ -21,7 +21,8 @@ inline unsigned ew_grid(long long n) {
   return (unsigned)g;
 }
 
-struct Lengths { float v[IKL_MAX_LINKS]; };
+constexpr int kFkMaxLinks = 8;          // the function-level FK also serves the reference's (broken) eight-link arm
+struct Lengths { float v[kFkMaxLinks]; };
 
 // Elements per thread per grid-stride step.  The penalty kernels read a few 4-byte elements per sample from strided column
 // views; with one sample per thread an SM has too few bytes in flight to cover the HBM latency (jl_forward: 41 % of the
@@ -241,29 +242,33 @@ extern "C" {
 
 IklStatus ikl_fk_forward(const float* theta, int64_t theta_sb, int64_t theta_sj, int64_t batch, int32_t num_links,
                          const float* link_length_host, float* tips_out, void* stream) {
-  if (batch < 0 || (num_links != 2 && num_links != 3)) return num_links < 1 || batch < 0 ? IKL_ERR_INVALID_ARGUMENT : IKL_ERR_UNSUPPORTED;
+  if (batch < 0 || num_links < 1) return IKL_ERR_INVALID_ARGUMENT;
+  if (num_links != 2 && num_links != 3 && num_links != 8) return IKL_ERR_UNSUPPORTED;
   if (batch == 0) return IKL_OK;
   if (!theta || !tips_out) return IKL_ERR_INVALID_ARGUMENT;
   Lengths L;
-  for (int m = 0; m < IKL_MAX_LINKS; ++m) L.v[m] = (link_length_host && m < num_links) ? link_length_host[m] : 1.0f;
+  for (int m = 0; m < kFkMaxLinks; ++m) L.v[m] = (link_length_host && m < num_links) ? link_length_host[m] : 1.0f;
   cudaStream_t st = (cudaStream_t)stream;
   count_launch();
   if (num_links == 3) fk_forward_kernel<3><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, tips_out);
-  else fk_forward_kernel<2><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, tips_out);
+  else if (num_links == 2) fk_forward_kernel<2><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, tips_out);
+  else fk_forward_kernel<8><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, tips_out);
   return cuda_status(cudaGetLastError());
 }
 
 IklStatus ikl_fk_backward(const float* theta, int64_t theta_sb, int64_t theta_sj, int64_t batch, int32_t num_links,
                           const float* link_length_host, const float* grad_tips, float* dtheta, void* stream) {
-  if (batch < 0 || (num_links != 2 && num_links != 3)) return num_links < 1 || batch < 0 ? IKL_ERR_INVALID_ARGUMENT : IKL_ERR_UNSUPPORTED;
+  if (batch < 0 || num_links < 1) return IKL_ERR_INVALID_ARGUMENT;
+  if (num_links != 2 && num_links != 3 && num_links != 8) return IKL_ERR_UNSUPPORTED;
   if (batch == 0) return IKL_OK;
   if (!theta || !grad_tips || !dtheta) return IKL_ERR_INVALID_ARGUMENT;
   Lengths L;
-  for (int m = 0; m < IKL_MAX_LINKS; ++m) L.v[m] = (link_length_host && m < num_links) ? link_length_host[m] : 1.0f;
+  for (int m = 0; m < kFkMaxLinks; ++m) L.v[m] = (link_length_host && m < num_links) ? link_length_host[m] : 1.0f;
   cudaStream_t st = (cudaStream_t)stream;
   count_launch();
   if (num_links == 3) fk_backward_kernel<3><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, grad_tips, dtheta);
-  else fk_backward_kernel<2><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, grad_tips, dtheta);
+  else if (num_links == 2) fk_backward_kernel<2><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, grad_tips, dtheta);
+  else fk_backward_kernel<8><<<ew_grid(batch), kEwThreads, 0, st>>>(theta, theta_sb, theta_sj, batch, L, grad_tips, dtheta);
   return cuda_status(cudaGetLastError());
 }
 

@@ -3,8 +3,7 @@ return conventions, computed by the CUDA kernels in libikl.so (ikl_fk_forward / 
 
 Reference interface replaced: kinematics/forward_kinematics.py:47-83 (ForwardKinematicsThreeLinkTorch),
 :7-44 (the NumPy scalar helpers) and :86-110 (the eight-link function, which cannot run in the reference:
-`batch_size` undefined at :99, `range()` without arguments at :104 -- the name is kept because
-scripts/trainer.py:13 and kinematics/dataset.py:6 import it).
+`batch_size` undefined at :99, `range()` without arguments at :104 -- here it is the function that loop spells out).
 """
 import numpy as np
 import torch
@@ -57,8 +56,13 @@ def ForwardKinematicsTwoLinkTorch(theta):
 
 
 def ForwardKinematicsEightLinkTorch(theta):
-  """Present for import compatibility only; the reference's version raises NameError at its first line of work."""
+  """theta (b, 8) -> the eight tips, each (b, 3) = (x, y, cumulative angle), end effector FIRST.
+
+  The reference's version cannot run (kinematics/forward_kinematics.py:99 uses an undefined `batch_size`, :104 calls
+  `range()` without arguments); this is the function its loop body spells out -- link i adds R8_LENGTH at the cumulative
+  angle, `links.reverse()` puts the end effector first (:105-110) -- computed by the same kernel as the 3-link arm.
+  No reference output exists to pin it against: its parity is pinned only by the NumPy restatement in the tests.
+  """
   assert(len(theta.shape) == 2)
   assert(theta.shape[1] == 8)
-  raise NotImplementedError("8-link forward kinematics does not run in the reference either "
-                            "(kinematics/forward_kinematics.py:99,104); only 2 and 3 links are supported")
+  return _ops.fk_forward_kinematics(theta, (Constants.R8_LENGTH,) * 8)

@@ -150,6 +150,40 @@ def test_fk_two_link_against_numpy_reference(cuda_device):
   assert np.allclose([float(v) for v in fk.ForwardKinematicsTwoLink(g["theta2"][3])], g["ee2_f64"][3])
 
 
+def test_fk_eight_link_repaired(cuda_device):
+  """ForwardKinematicsEightLinkTorch: the reference's function cannot run (forward_kinematics.py:99,104); ours computes
+  what its loop body spells out.  Pinned against that loop restated in torch (fp32 values to 1e-5 of the reach, gradient
+  against autograd of the restatement in fp64) -- there is no reference output to compare with."""
+  from kinematics.forward_kinematics import ForwardKinematicsEightLinkTorch
+
+  def intended(theta):                    # forward_kinematics.py:98-110 with batch_size = theta.shape[0], range(1, 8)
+    links = [None] * 8
+    phi = theta[:, 0]
+    links[0] = torch.stack([torch.cos(phi), torch.sin(phi), phi], dim=1)
+    for i in range(1, 8):
+      phi = theta[:, i] + links[i - 1][:, 2]
+      links[i] = torch.stack([links[i - 1][:, 0] + torch.cos(phi), links[i - 1][:, 1] + torch.sin(phi), phi], dim=1)
+    links.reverse()
+    return links
+
+  g = torch.Generator().manual_seed(8)
+  theta = (torch.rand(3001, 8, generator=g) * 2 - 1) * 2.5
+  got = ForwardKinematicsEightLinkTorch(theta.to(cuda_device))
+  want = intended(theta)
+  assert len(got) == 8
+  for a, b in zip(got, want):
+    assert a.shape == (3001, 3)
+    close(a.cpu().numpy(), b.numpy(), scale=8.0)
+  th_g = theta.to(cuda_device).requires_grad_(True)
+  w = [torch.randn(3001, 3, generator=g) for _ in range(8)]
+  sum((t * wk.to(cuda_device)).sum() for t, wk in zip(ForwardKinematicsEightLinkTorch(th_g), w)).backward()
+  th_r = theta.double().requires_grad_(True)
+  sum((t * wk.double()).sum() for t, wk in zip(intended(th_r), w)).backward()
+  close(th_g.grad.cpu().numpy(), th_r.grad.numpy(), scale=float(th_r.grad.abs().max()))
+  with pytest.raises(AssertionError):
+    ForwardKinematicsEightLinkTorch(theta[:, :3].to(cuda_device))
+
+
 def test_fk_backward_matches_autograd_of_oracle(cuda_device):
   import kinematics.forward_kinematics as fk
   torch.manual_seed(3)

@@ -12,5 +12,7 @@ timeout 900 python tools/kernel_bench.py > gpurun_out/kernel_table.jsonl 2> gpur
 if [ "$1" = "ncu" ]; then
   timeout 300 python tools/profile_target.py 24 planes > gpurun_out/plain.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:lagrangian -s 2 -c 1 -o gpurun_out/prof_planes python tools/profile_target.py 24 planes > gpurun_out/ncu_full.log 2>&1
+  timeout 300 python tools/profile_target.py 24 rows > gpurun_out/plain_rows.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:lagrangian -s 2 -c 1 -o gpurun_out/prof_rows python tools/profile_target.py 24 rows > gpurun_out/ncu_full_rows.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 20 --warmup 3 --skip-e2e --skip-cpu --skip-train-step --skip-context > gpurun_out/ncu_bench.log 2>&1
 fi
