@@ -32,7 +32,7 @@ def measure(args):
   except Exception:
     pass
   cases = [("cfg_joint_limits_and_4obs_dynamic", 80, 68), ("cfg_joint_limits_and_4obs_static", 32, 20),
-           ("cfg_joint_limits", 32, 20), ("cfg_no_constraints", 32, 20)]
+           ("cfg_joint_limits_and_1obs_static", 32, 20), ("cfg_joint_limits", 32, 20), ("cfg_no_constraints", 32, 20)]
   if args.quick:
     cases = cases[:1]
   if args.configs:
