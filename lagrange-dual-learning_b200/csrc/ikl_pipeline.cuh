@@ -79,30 +79,65 @@ struct TmaLayout {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
 };
 
+// The gradient kernels' slow path: a pair that eval_pair<!EXACT> reported as within ~8 ulp of a tie (a tip on an obstacle's
+// circle) is re-read from global memory through the generic strides, evaluated with exact distances and its d/dtheta
+// stored again.  Not inlined: it costs the hot loop no registers, and it runs for about one pair in a million.
+template <class C, class W2>
+static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, const W2& w2, long long bA, long long bB) {
+  f2 th[3], ob[C::NOB][3], acc[C::K], dth[3], ee[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) th[j] = f2_make(p.theta[bA * p.th_sb + j * p.th_sj], p.theta[bB * p.th_sb + j * p.th_sj]);
+  const f2 tx = f2_make(p.target[bA * p.tg_sb], p.target[bB * p.tg_sb]);
+  const f2 ty = f2_make(p.target[bA * p.tg_sb + p.tg_sc], p.target[bB * p.tg_sb + p.tg_sc]);
+  if (C::DYN) {
+#pragma unroll
+    for (int k = 0; k < C::NOBS; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        ob[k][c] = f2_make(p.obst[bA * p.ob_sb + k * p.ob_so + c * p.ob_sc], p.obst[bB * p.ob_sb + k * p.ob_so + c * p.ob_sc]);
+    }
+  } else {
+    static_obstacles_packed<C>(p, ob);
+  }
+#pragma unroll
+  for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
+  eval_pair<C::NOBS, C::JL, true, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    p.dtheta[bA * p.dt_sb + j * p.dt_sj] = f2_lo(dth[j]);
+    p.dtheta[bB * p.dt_sb + j * p.dt_sj] = f2_hi(dth[j]);
+  }
+}
+
 // ---- what a pipeline does with a pair of samples ----------------------------------------------------------------------
 // The two staged pipelines (run_planes_pipe, run_rows_pipe) hand every pair of samples to a "body":
 //   pair(th, tx, ty, ob, bA, bB)   operands of samples bA and bB (packed: lo half = bA, hi half = bB)
 //   tile_done()                    once per tile, by every thread of the block (also by threads without a valid pair)
 //   finish()                       after the last tile
-// LagrangianBody: the K running sums (+ d/dtheta).  `r`: the rows pipeline keeps obstacle (k ^ r) in slot k.
+// LagrangianBody: the K running sums (+ d/dtheta).  `r`: the rows pipeline keeps obstacle (k ^ r) in slot k; `w2` are the
+// multipliers in that slot order, `w2_plain` in constraint order (for the exact redo of a near-tie pair).
 template <class C, class W2>
 struct LagrangianBody {
   const LagrangianParams& p;
   const W2& w2;
+  const W2& w2_plain;
   WarpSharedAcc<C::K>& sacc;
   const int r;
   f2 acc[C::K];
   int since_flush;
   static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
   static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
-  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, WarpSharedAcc<C::K>& sa, int rr)
-      : p(pp), w2(w), sacc(sa), r(rr), since_flush(0) {
+  // cheap distances (see ikl_packed.cuh) in the forward-only and the gradient kernels alike, so both report the same
+  // sums bit for bit; the gradient kernels redo near-tie pairs exactly
+  static constexpr bool kExact = C::NOBS == 0 || IKL_EXACT_GRAD;
+  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, const W2& w_plain, WarpSharedAcc<C::K>& sa, int rr)
+      : p(pp), w2(w), w2_plain(w_plain), sacc(sa), r(rr), since_flush(0) {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
   }
   __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
     f2 dth[3], ee[3];
-    eval_pair<C::NOBS, C::JL, C::GRAD>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
     if (C::GRAD) {
       if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
 #pragma unroll
@@ -118,6 +153,9 @@ struct LagrangianBody {
       }
     } else {
       store_side_outputs(p, bA, bB, ee, tx, ty);
+    }
+    if constexpr (!kExact && C::GRAD) {
+      if (near_tie) redo_pair_exact<C>(p, w2_plain, bA, bB);
     }
   }
   __device__ __forceinline__ void flush() {
@@ -167,7 +205,7 @@ struct StatsBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
     const PackedHostWeights w2{p.pu};
-    eval_pair<C::NOBS, C::JL, false>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    eval_pair<C::NOBS, C::JL, false, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
     float v[C::K];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
@@ -350,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
   }
   WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
   auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, 0);
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0);
     run_planes_pipe<C>(p, body, dyn_smem, bars);
   };
   if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
@@ -496,12 +534,12 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_
     }
   }
   WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
-  auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, sacc, r);
+  auto run = [&](const auto& w2, const auto& w2_plain) {
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r);
     run_rows_pipe<C>(p, body, dyn_smem, bars, r);
   };
-  if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]});
-  else run(PackedHostWeights{p.pu});
+  if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]}, PackedSmemWeights{s_lam_perm[0]});     // table 0: k ^ 0 = k
+  else run(PackedHostWeights{p.pu}, PackedHostWeights{p.pu});
   // ragged tail (< 512 samples), one sample per thread through the scalar code
   {
     const long long full = (p.batch / kTmaTile) * kTmaTile;

@@ -603,6 +603,64 @@ def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
     close(dth[2], dth64[2], scale=np.abs(dth64).max(), rtol=2e-6)
 
 
+def test_ties_through_the_staged_kernels(cuda_device, monkeypatch):
+  """The gradient kernels of the staged pipelines use cheap (~3 ulp) distances and redo the rare near-tie pairs exactly:
+  samples with a tip EXACTLY on a circle (d == r, torch splits the gradient evenly), a few ulp either side of it, joints
+  exactly on a limit and a tip on a centre, scattered through batches big enough for the staged rows / planes kernels,
+  must come out like the all-exact direct-load kernels bit for bit (planes) / to round-off (staged rows)."""
+  from ikl import fused, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
+  dev = cuda_device
+  B = 2048
+  theta, q_des, obst = synthetic.make_batch(B, seed=77)
+  lim = float(np.float32(2.094395))
+  r = np.float32(0.4)
+  special = list(range(5, B, 97))
+  for n, b in enumerate(special):
+    theta[b] = torch.tensor([0.0, 0.0, 0.0])               # tips (1,0), (2,0), (3,0)
+    obst[b, :, 0] = 10.0
+    obst[b, :, 2] = float(r)
+    kind = n % 5
+    if kind == 0:
+      obst[b, n % 4, :3] = torch.tensor([2.0, float(r), float(r)])                       # d == r exactly
+    elif kind == 1:
+      obst[b, n % 4, :3] = torch.tensor([2.0, float(np.nextafter(r, np.float32(1))), float(r)])   # one ulp outside
+    elif kind == 2:
+      obst[b, n % 4, :3] = torch.tensor([2.0, float(np.nextafter(r, np.float32(0))), float(r)])   # one ulp inside
+    elif kind == 3:
+      theta[b] = torch.tensor([lim, -lim, 0.0])                                          # joints exactly on the limits
+    else:
+      obst[b, n % 4, :3] = torch.tensor([1.0, 0.0, float(r)])                            # tip exactly on a centre
+  lam = (0.5 + 0.1 * np.arange(16)).astype(np.float32)
+  th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+  planes = synthetic.to_planes(th, qd, ob)
+  # all-exact partners: the direct-load kernels
+  monkeypatch.setenv("IKL_ROWS_TMA", "0")
+  monkeypatch.setenv("IKL_PLANES_TMA", "0")
+  v_x, _, d_x = fused.lagrangian_forward_backward(spec, th, qd, ob, lam.tolist())
+  assert "<rows," in _cabi.last_kernel_name()
+  v_px, _, d_px = fused.lagrangian_forward_backward(spec, *planes, lam.tolist())
+  assert "<planes," in _cabi.last_kernel_name() and torch.equal(d_px.contiguous(), d_x)
+  monkeypatch.delenv("IKL_ROWS_TMA")
+  monkeypatch.delenv("IKL_PLANES_TMA")
+  for weights in (lam.tolist(), torch.from_numpy(lam).to(dev)):
+    v_p, _, d_p = fused.lagrangian_forward_backward(spec, *planes, weights)
+    assert "<planes_tma," in _cabi.last_kernel_name()
+    assert torch.equal(d_p.contiguous(), d_x), "staged planes kernel must reproduce the exact kernels' gradient bits, ties included"
+    v_r, _, d_r = fused.lagrangian_forward_backward(spec, th, qd, ob, weights)
+    assert "<rows_tma," in _cabi.last_kernel_name()
+    assert float((d_r - d_x).abs().max()) <= 1e-6 * float(d_x.abs().max())
+    assert torch.equal(d_r[special], d_x[special]), "redone pairs are evaluated in plain obstacle order"
+    for v in (v_p, v_r):
+      assert float((v - v_x).abs().max()) <= 2e-6 * float(v_x.abs().max())
+  # and against torch itself on the special samples (NaN at the centre case excluded)
+  ref = O.lagrangian_with_grad(theta[special], q_des[special], torch.from_numpy(lam), ospec, obst[special])["dtheta"]
+  ok = ~torch.isnan(ref).any(dim=1)
+  assert int(ok.sum()) >= len(special) * 3 // 5
+  close(d_x[special].cpu()[ok].numpy(), ref[ok].numpy(), scale=float(ref[ok].abs().max()), rtol=2e-6)
+
+
 def test_autograd_function_and_general_upstream_gradients(cuda_device):
   from ikl import fused, synthetic
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
