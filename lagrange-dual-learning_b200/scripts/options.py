@@ -45,6 +45,10 @@ class Options(object):
                              help="Generate the datasets on the GPU and batch them there (for large batch sizes)")
     self.parser.add_argument("--cuda_graph", action="store_true", default=False,
                              help="Replay each train step (network, fused Lagrangian, backward, Adam) as one CUDA graph")
+    self.parser.add_argument("--val_batch_size", type=int, default=0,
+                             help="Batch size of the validation loader (dual step and validation pass); 0 = --batch_size as in "
+                                  "the reference.  The sums are additive, so a few large batches give the same dual step "
+                                  "(up to the dropout draws of the reference's train-mode validation) in far fewer launches")
     self.parser.add_argument("--load_multipliers", action="store_true", default=False,
                              help="Also reload multipliers.pth from --load_weights_folder (the reference restarts lambda)")
 

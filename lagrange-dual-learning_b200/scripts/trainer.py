@@ -167,13 +167,14 @@ class IkLagrangeDualTrainer(object):
       self.train_dataset = IkDataset(self.opt.train_dataset_size, self.opt.num_links, self.json_config, cache_save_path=train_cache)
       self.val_dataset = IkDataset(self.opt.val_dataset_size, self.opt.num_links, self.json_config, cache_save_path=val_cache)
 
+    val_batch = getattr(self.opt, "val_batch_size", 0) or self.opt.batch_size
     if getattr(self.opt, "device_data", False):
       from ikl.device_loader import DeviceBatchLoader
       self.train_loader = DeviceBatchLoader(self.train_dataset, self.opt.batch_size, True, device=self.device, seed=11, planes=True)
-      self.val_loader = DeviceBatchLoader(self.val_dataset, self.opt.batch_size, True, device=self.device, seed=12, planes=True)
+      self.val_loader = DeviceBatchLoader(self.val_dataset, val_batch, True, device=self.device, seed=12, planes=True)
     else:
       self.train_loader = ikl_dist.make_loader(self.train_dataset, self.opt.batch_size, self.opt.num_workers)
-      self.val_loader = ikl_dist.make_loader(self.val_dataset, self.opt.batch_size, self.opt.num_workers)
+      self.val_loader = ikl_dist.make_loader(self.val_dataset, val_batch, self.opt.num_workers)
 
   # ---------------------------------------------------------------------------------------------------------------
   def _host_multipliers(self, lamda):

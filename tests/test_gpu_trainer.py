@@ -256,6 +256,22 @@ def test_eval_stats_match_per_sample_oracle(cuda_device, monkeypatch):
       assert abs(float(err) - float(want_err)) <= 1e-5 * float(want_err)
 
 
+def test_val_batch_size_gives_the_same_dual_step(tmp_path, cuda_device):
+  """--val_batch_size: the dual step over the validation set in ONE launch instead of one per 8 examples -- the sums are
+  additive, so lambda moves the same way (dropout is off in the fixtures; the reference's train-mode validation would draw
+  different masks)."""
+  name = "cfg_joint_limits_and_4obs_dynamic"
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  small = make_trainer(name, tmp_path / "small", fx, extra=("--val_batch_size", "8"))
+  n_val = len(small.val_dataset)
+  big = make_trainer(name, tmp_path / "big", fx, extra=("--val_batch_size", str(n_val)))
+  assert len(big.val_loader) == 1 and len(small.val_loader) > 1
+  lam_s = small.update_multipliers(small.lambda_multipliers)
+  lam_b = big.update_multipliers(big.lambda_multipliers)
+  assert float((lam_s - lam_b).abs().max()) <= 1e-6 * float(lam_s.abs().max())
+  assert not torch.equal(lam_s, small.lambda_multipliers)
+
+
 def test_cuda_graph_train_step_matches_eager(tmp_path, cuda_device):
   """--cuda_graph replays forward + fused Lagrangian + backward + Adam as one graph; same weights and lambda as eager."""
   name = "cfg_joint_limits_and_4obs_dynamic"
