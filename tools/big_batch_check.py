@@ -18,4 +18,9 @@ for name,v in (('rows',v_rows),('planes',v_pl)):
     err=np.abs(v.cpu().numpy()-sums)/abs_sums
     print(name,'max err rel to sum|term| %.2e'%err.max())
 full=(B//512)*512
-print('dtheta rows vs planes bitwise on full tiles:', torch.equal(d_rows[:full], d_pl.contiguous()[:full]), ' tail max diff %.2e'%float((d_rows[full:]-d_pl.contiguous()[full:]).abs().max()))
+dpl=d_pl.contiguous()
+print('dtheta staged rows vs staged planes: max |diff| / max |dtheta| = %.2e  (staged rows adds the obstacle forces in the order k ^ r)' % (float((d_rows-dpl).abs().max())/float(dpl.abs().max())))
+import os
+os.environ['IKL_ROWS_TMA']='0'
+v_d,l_d,d_d=fused.lagrangian_forward_backward(spec,theta,q_des,obst,lam); k3=_cabi.last_kernel_name()
+print(k3, 'dtheta direct rows vs staged planes bitwise on full tiles:', torch.equal(d_d[:full], dpl[:full]), ' tail max diff %.2e'%float((d_d[full:]-dpl[full:]).abs().max()))
