@@ -118,6 +118,7 @@ void fill_packed_uniforms(const IklSpec* spec, const Uniforms& u, PackedUniforms
   pu.ob_ndiff = dup(u.ob_lo - u.ob_hi);
   for (int o = 0; o < kMaxObst; ++o)
     for (int c = 0; c < 3; ++c) pu.stat_ob[o][c] = dup(u.stat_ob[o][c]);
+  for (int o = 0; o < kMaxObst; ++o) pu.stat_thr[o] = dup(u.stat_ob[o][2] * kNearTie);      // fl(r * 2^-20): exact scaling
   for (int i = 0; i < kMaxK; ++i) pu.lam[i] = dup(u.w[i]);
 }
 

@@ -101,7 +101,7 @@ static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, c
   }
 #pragma unroll
   for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  eval_pair<C::NOBS, C::JL, true, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+  eval_pair<C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     p.dtheta[bA * p.dt_sb + j * p.dt_sj] = f2_lo(dth[j]);
@@ -137,7 +137,7 @@ struct LagrangianBody {
   }
   __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
     f2 dth[3], ee[3];
-    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
     if (C::GRAD) {
       if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
 #pragma unroll
@@ -205,7 +205,7 @@ struct StatsBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
     const PackedHostWeights w2{p.pu};
-    eval_pair<C::NOBS, C::JL, false, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    eval_pair<C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
     float v[C::K];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
