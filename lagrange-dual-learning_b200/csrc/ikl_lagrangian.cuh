@@ -426,7 +426,7 @@ __device__ __forceinline__ void run_planes_packed(const LagrangianParams& p, con
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
@@ -476,7 +476,7 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
       float* dA = p.dtheta + bA * 3;
       float* dB = p.dtheta + bB * 3;

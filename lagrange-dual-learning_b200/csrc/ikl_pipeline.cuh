@@ -101,7 +101,7 @@ static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, c
   }
 #pragma unroll
   for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  eval_pair<C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+  eval_pair<C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     p.dtheta[bA * p.dt_sb + j * p.dt_sj] = f2_lo(dth[j]);
@@ -123,6 +123,7 @@ struct LagrangianBody {
   const W2& w2_plain;
   WarpSharedAcc<C::K>& sacc;
   const int r;
+  const f2 ndiff;                 // lo - hi slope of the circle penalty, in registers (see eval_pair)
   f2 acc[C::K];
   int since_flush;
   static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
@@ -130,14 +131,15 @@ struct LagrangianBody {
   // cheap distances (see ikl_packed.cuh) in the forward-only and the gradient kernels alike, so both report the same
   // sums bit for bit; the gradient kernels redo near-tie pairs exactly
   static constexpr bool kExact = C::NOBS == 0 || IKL_EXACT_GRAD;
-  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, const W2& w_plain, WarpSharedAcc<C::K>& sa, int rr)
-      : p(pp), w2(w), w2_plain(w_plain), sacc(sa), r(rr), since_flush(0) {
+  __device__ __forceinline__ LagrangianBody(const LagrangianParams& pp, const W2& w, const W2& w_plain, WarpSharedAcc<C::K>& sa, int rr,
+                                            const volatile float2* s_ndiff)
+      : p(pp), w2(w), w2_plain(w_plain), sacc(sa), r(rr), ndiff(C::DYN ? as_f2(pp.pu.ob_ndiff) : f2_make(s_ndiff->x, s_ndiff->y)), since_flush(0) {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
   }
   __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
     f2 dth[3], ee[3];
-    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, ndiff);
     if (C::GRAD) {
       if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
 #pragma unroll
@@ -205,7 +207,7 @@ struct StatsBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
     const PackedHostWeights w2{p.pu};
-    eval_pair<C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee);
+    eval_pair<C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     float v[C::K];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
@@ -386,9 +388,12 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
       s_lam2[threadIdx.x] = make_float2(l, l);
     }
   }
+  __shared__ float2 s_ndiff;
+  if (threadIdx.x == 0) s_ndiff = p.pu.ob_ndiff;
   WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
+  __syncthreads();
   auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0);
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0, &s_ndiff);
     run_planes_pipe<C>(p, body, dyn_smem, bars);
   };
   if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
@@ -534,8 +539,11 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_
     }
   }
   WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
+  __shared__ float2 s_ndiff;
+  if (threadIdx.x == 0) s_ndiff = p.pu.ob_ndiff;
+  __syncthreads();
   auto run = [&](const auto& w2, const auto& w2_plain) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r);
+    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r, &s_ndiff);
     run_rows_pipe<C>(p, body, dyn_smem, bars, r);
   };
   if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]}, PackedSmemWeights{s_lam_perm[0]});     // table 0: k ^ 0 = k
