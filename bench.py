@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "lagrange-dual-learning_b200")
 for p in (ROOT, PKG):
   if p not in sys.path:
-    sys.path.insert(0, p)
+    sys.path.insert(0, p)          # (--impl reference with baseline/_ref takes PKG off the path again: ref_harness)
 
 METRIC = "fk_penalty_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
@@ -160,24 +160,112 @@ def cpu_c_oracle_samples_per_s(batch_log2):
           "sample": "oracle/ik_oracle.c (C + OpenMP, fp32 maths, closed-form gradient) on a 2^%d-sample batch, best of 5" % batch_log2}
 
 
+SHIPPED_LAMBDA_OBS4_DYN = [4.060915, 0.0, 0.0, 0.280665, 0.0, 0.0, 1.449509, 0.0, 0.0, 1.679491, 0.0, 0.0, 1.564413,
+                           0.0, 0.0, 1.505343]   # resources/pretrained_models/ik_threelink_obs4_dyn/models/weights_650/multipliers.pth
+
+
+def reference_tree_samples_per_s(batch_log2, steps, warmup):
+  """The UNMODIFIED reference (baseline/_ref, installed by tools/install_ref.py) on the host cores: its own
+  IkLagrangeDualTrainer.process_batch (scripts/trainer.py:159-249) over its own kinematics/*.py, then
+  lagrange_loss.backward() (trainer.py:264), with theta as a leaf in place of the network (the MLP is not part of the
+  hot path).  Nothing of this repo's product tree is importable in this process (ref_harness removes it from sys.path)."""
+  import tempfile
+  import torch
+  from baseline import ref_harness as H
+  trainer_mod, options_mod = H.load_reference_scripts(dropin=False)
+  H.assert_resolution(trainer_mod, dropin=False)
+  assert trainer_mod.device == "cpu"
+  torch.set_num_threads(os.cpu_count() or 1)
+  B = 1 << batch_log2
+  tmp = tempfile.mkdtemp(prefix="ikl_ref_arm_")
+  opt = H.reference_options(options_mod, [
+      "--model_name", "bench", "--config_file", os.path.join(H.REF_TREE, "resources", CONFIG_NAME + ".json"), "--log_dir", tmp,
+      "--num_workers", "0", "--train_dataset_size", "8", "--val_dataset_size", "8", "--penalty_good_slope", str(GOOD_SLOPE),
+      "--penalty_bad_slope", str(BAD_SLOPE)])
+  import contextlib
+  with H.git_worktree(tmp), contextlib.redirect_stdout(sys.stderr):     # the trainer's banner must not share stdout with the JSON line
+    tr = trainer_mod.IkLagrangeDualTrainer(opt)
+  # the synthetic batch of ikl.synthetic.make_batch (SURVEY 8d), restated here because that package is out of reach
+  g = torch.Generator().manual_seed(0)
+  theta = (torch.rand(B, 3, generator=g) * 2 - 1) * 2.5
+  phi = torch.cumsum((torch.rand(B, 3, generator=g) * 2 - 1) * 2.094395, dim=1)
+  obst = torch.zeros(B, 4, 4)
+  obst[:, :, :2] = (torch.rand(B, 4, 2, generator=g) * 2 - 1) * 1.2
+  obst[:, :, 2] = 0.4
+  q_des = torch.stack([torch.cos(phi).sum(1), torch.sin(phi).sum(1), phi[:, -1]], dim=1)
+  lam = torch.tensor(SHIPPED_LAMBDA_OBS4_DYN)
+
+  class ThetaLeaf(torch.nn.Module):
+    def __init__(self):
+      super().__init__()
+      self.theta = torch.nn.Parameter(theta)
+
+    def forward(self, x):
+      return self.theta
+  tr.model = ThetaLeaf()
+  x = torch.zeros(B, 20)
+
+  def step():
+    out = tr.process_batch({"input_tensor": x, "q_ee_desired": q_des, "dynamic_obstacles": obst}, lam)
+    tr.model.zero_grad()
+    out["lagrange_loss"].backward()
+  for _ in range(warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    step()
+  dt = (time.perf_counter() - t0) / steps
+  return B / dt, dt, torch.get_num_threads(), B
+
+
+def cpu_baseline_leg(args):
+  """cpu_baseline of the ours arm: the reference's own code from baseline/_ref in a fresh process (so that its `kinematics`
+  package, not this repo's drop-in, is the one imported) on a bounded 2^cpu_batch_log2 sample; the oracle port in-process
+  when the reference tree is not installed."""
+  if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "scripts", "trainer.py")):
+    try:
+      r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5", "--warmup", "1",
+                          "--cpu-batch-log2", str(args.cpu_batch_log2)], capture_output=True, text=True, timeout=600,
+                         env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+      ref_line = json.loads(r.stdout.strip().splitlines()[-1])
+      return ref_line["cpu_baseline"]
+    except Exception as e:
+      sys.stderr.write("cpu_baseline: reference subprocess failed (%s); timing the oracle port instead\n" % (e,))
+  sps, dtc, cores, Bc = cpu_oracle_samples_per_s(args.cpu_batch_log2, 5, 1)
+  return {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32) on a 2^%d-sample "
+                    "batch of the same workload, mean of 5 after 1 warm-up (%.0f ms each)" % (args.cpu_batch_log2, dtc * 1e3)}
+
+
 def run_reference(args):
   """--impl reference: the reference's CPU path (PyTorch eager forward + autograd backward, fp32, all host threads),
-  exactly K timed steps after W warm-ups; the per-step sample is sized so that the run stays within minutes."""
+  exactly K timed steps after W warm-ups; the per-step sample is sized so that the run stays within minutes.  With
+  baseline/_ref present (tools/install_ref.py) it is the reference's own code (`kind: "reference"`); otherwise the oracle
+  port of it (`kind: "port"`, bit-identical outputs: tests/test_oracle_pinned.py)."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  os.environ["CUDA_VISIBLE_DEVICES"] = ""        # this arm is the host-core path; the reference would otherwise pick the GPU
   steps, warmup = max(args.steps, 1), max(args.warmup, 1)
   batch_log2 = args.cpu_batch_log2 if steps <= 50 else (args.cpu_batch_log2 - 2 if steps <= 500 else args.cpu_batch_log2 - 4)
-  sps, dt, cores, B = cpu_oracle_samples_per_s(batch_log2, steps, warmup)
-  sample = "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32), batch 2^%d per step, %d steps" % (
-      batch_log2, steps)
+  have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "scripts", "trainer.py")) and not args.force_port
+  if have_ref:
+    sps, dt, cores, B = reference_tree_samples_per_s(batch_log2, steps, warmup)
+    kind = "reference"
+    sample = ("the unmodified reference from baseline/_ref: IkLagrangeDualTrainer.process_batch (scripts/trainer.py:159-249) + "
+              "lagrange_loss.backward(), theta as a leaf, fp32, batch 2^%d per step, %d steps" % (batch_log2, steps))
+  else:
+    sps, dt, cores, B = cpu_oracle_samples_per_s(batch_log2, steps, warmup)
+    kind = "port"
+    sample = "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32), batch 2^%d per step, %d steps" % (
+        batch_log2, steps)
   line = {
       "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
       "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
       "config": {"workload": "three_link_arm + %s, K=16: FK+penalty+Lagrangian fwd+bwd, synthetic theta/target/obstacle batches" % CONFIG_NAME,
                  "batch_per_step": B, "device": "cpu", "note": "bounded sample of the 2^24-per-GPU workload of the ours arm"},
-      "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+      "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
       "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
@@ -520,10 +608,7 @@ def run_ours(args):
     line["train_step_batch8"] = small
     line["context"] = extras
     if not args.skip_cpu and world == 1:
-      sps, dtc, cores, Bc = cpu_oracle_samples_per_s(args.cpu_batch_log2, 5, 1)
-      line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                              "sample": "oracle port of the reference PyTorch-eager CPU path (fwd + autograd bwd, fp32) on a 2^%d-sample "
-                                        "batch of the same workload, mean of 5 after 1 warm-up (%.0f ms each)" % (args.cpu_batch_log2, dtc * 1e3)}
+      line["cpu_baseline"] = cpu_baseline_leg(args)
       try:
         line["cpu_baseline_c"] = cpu_c_oracle_samples_per_s(args.cpu_batch_log2 + 1)
       except Exception as e:          # no C compiler on the box: the PyTorch port above is the baseline of record
@@ -551,6 +636,7 @@ def main():
   ap.add_argument("--skip-context", action="store_true")
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
+  ap.add_argument("--force-port", action="store_true", help="--impl reference: time the oracle port even when baseline/_ref is installed")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

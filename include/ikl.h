@@ -138,7 +138,9 @@ IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const
 IklStatus ikl_dual_update(const float* lam_in, const double* viol_sum, const float* viol_sum_f32,
                           float multiplier_lr, int32_t num_constraints, float* lam_out, void* stream);
 
-/* ---- function-level drop-ins (let an unchanged scripts/trainer.py reach CUDA op by op) ---------- */
+/* ---- function-level drop-ins (let an unchanged scripts/trainer.py reach CUDA op by op) ----------
+ * float32 only.  The reference's Python functions are dtype-generic (torch evaluates a float64 tensor in float64); the
+ * Python wrappers (ikl/ops.py) refuse any other dtype with a TypeError rather than narrowing it silently. */
 
 /* kinematics/forward_kinematics.py:47-83 ForwardKinematicsThreeLinkTorch (num_links 3; also 2: the maths of :7-22, and
  * 8: what the reference's non-running eight-link function :86-110 spells out).

@@ -6,14 +6,17 @@ The reference pushes the validation set through process_batch one example at a t
 constraint vector on the host; here the whole set goes through the network in large batches and ikl_eval_stats does
 the thresholding and counting on the device.
 
-  python scripts/evaluation/evaluate_ik_solutions.py --model_name NAME --config_file CFG --load_weights_folder DIR [...]
+  python lagrange-dual-learning_b200/fused_overlay/scripts/evaluation/evaluate_ik_solutions.py --model_name NAME --config_file CFG --load_weights_folder DIR [...]
 """
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.realpath(__file__)), "..", "..")))
+_OVERLAY = os.path.abspath(os.path.join(os.path.dirname(os.path.realpath(__file__)), "..", ".."))
+for _p in (os.path.dirname(_OVERLAY), _OVERLAY):        # package root (ikl, kinematics, utils, models), then this overlay (scripts)
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
 
 from ikl.device_data import eval_stats  # noqa: E402
 from scripts.options import Options  # noqa: E402

@@ -89,15 +89,18 @@ def load(path=None):
     if _lib is not None and (path is None or path == _lib_path):
       return _lib
     p = path or default_lib_path()
-    if not os.path.exists(p):
-      if os.environ.get("IKL_LIB"):
-        raise RuntimeError("IKL_LIB=%s does not exist" % p)
+    if path is None and not os.environ.get("IKL_LIB"):
+      # the default in-tree library must match the sources in the tree: rebuild when they changed (a no-op when the
+      # stamp matches), and never run stale kernels silently
       from . import build as _build
-      try:
-        p = _build.build()
-      except Exception as e:  # no nvcc, compile error ...
-        raise RuntimeError("libikl.so is not built and could not be built (%s). The IK Lagrangian path has no CPU "
-                           "fallback: run `python lagrange-dual-learning_b200/ikl/build.py`." % (e,))
+      if not _build.is_current():
+        try:
+          p = _build.build()
+        except Exception as e:  # no nvcc, compile error ...
+          raise RuntimeError("libikl.so is missing or older than csrc/ and could not be rebuilt (%s). The IK Lagrangian path "
+                             "has no CPU fallback: run `python lagrange-dual-learning_b200/ikl/build.py`." % (e,))
+    elif not os.path.exists(p):
+      raise RuntimeError("%s does not exist" % p)
     lib = ctypes.CDLL(p)
     for name, (res, args) in _SIGNATURES.items():
       fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly

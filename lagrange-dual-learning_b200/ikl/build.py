@@ -61,15 +61,33 @@ def _compile_one(args):
   return src, r.returncode, r.stdout
 
 
+def is_current(variant="", defines=()):
+  """True when libikl[_variant].so exists and was built from exactly the sources, headers and flags in the tree now."""
+  out = lib_path(variant)
+  stamp_file = out + ".stamp"
+  return os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == _stamp(defines)
+
+
 def build(force=False, variant="", defines=(), verbose=False):
-  """Compile every csrc/*.cu for sm_100a and link libikl[_variant].so.  Returns its path."""
-  nvcc = nvcc_path()
+  """Compile every csrc/*.cu for sm_100a and link libikl[_variant].so.  Returns its path.  Serialised across processes by
+  a file lock (torchrun starts one process per GPU; only the first one compiles)."""
+  import fcntl
   os.makedirs(LIB_DIR, exist_ok=True)
+  with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      return _build_locked(force, variant, defines, verbose)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, variant, defines, verbose):
   out = lib_path(variant)
   stamp_file = out + ".stamp"
   stamp = _stamp(defines)
   if not force and os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
     return out
+  nvcc = nvcc_path()
   obj_dir = os.path.join(PKG_DIR, "build", "obj_" + (variant or "default"))
   os.makedirs(obj_dir, exist_ok=True)
   jobs = [(nvcc, s, os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o"), tuple(defines)) for s in _sources()]
@@ -84,7 +102,8 @@ def build(force=False, variant="", defines=(), verbose=False):
     f.write("\n".join(logs))
   if verbose:
     print("\n".join(logs))
-  link = [nvcc] + ARCH_FLAGS + ["-shared", "-o", out] + [j[2] for j in jobs] + ["-cudart", "static"]
+  # the static CUDA runtime stays private to the library: only the ikl_* ABI of include/ikl.h is exported
+  link = [nvcc] + ARCH_FLAGS + ["-shared", "-o", out] + [j[2] for j in jobs] + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
   r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   if r.returncode != 0:
     sys.stderr.write(r.stdout)

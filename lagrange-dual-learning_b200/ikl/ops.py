@@ -26,6 +26,14 @@ def _device_for(*tensors):
   return torch.device("cuda", torch.cuda.current_device())
 
 
+def _require_f32(t, name):
+  """The kernels compute in float32 only.  The reference's functions are dtype-generic (a float64 tensor is evaluated in
+  float64 by torch); silently narrowing such an input would be different arithmetic, so it is refused instead."""
+  if isinstance(t, torch.Tensor) and t.dtype != torch.float32:
+    raise TypeError("%s is %s: the CUDA drop-ins compute in float32 only (include/ikl.h); cast explicitly with .float() "
+                    "if float32 arithmetic is what you want" % (name, t.dtype))
+
+
 def _stream(dev):
   return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -72,12 +80,13 @@ class _ForwardKinematics(torch.autograd.Function):
 def fk_forward_kinematics(theta, link_lengths=None):
   """theta (B,J) -> tuple of J (B,3) tensors, END EFFECTOR FIRST, rows (x, y, cumulative angle)."""
   assert len(theta.shape) == 2                      # forward_kinematics.py:57
-  src_device, src_dtype = theta.device, theta.dtype
+  _require_f32(theta, "theta")
+  src_device = theta.device
   dev = _device_for(theta)
-  th = theta.to(device=dev, dtype=torch.float32)
+  th = theta.to(device=dev)
   tips = _ForwardKinematics.apply(th, None if link_lengths is None else tuple(link_lengths))
-  if src_device != dev or src_dtype != torch.float32:
-    tips = tuple(t.to(device=src_device, dtype=src_dtype) for t in tips)
+  if src_device != dev:
+    tips = tuple(t.to(device=src_device) for t in tips)
   return tips
 
 
@@ -98,10 +107,11 @@ def _flat_view(t, shape):
 
 def _prep(dev, *ts):
   out = []
-  for t in ts:
+  for i, t in enumerate(ts):
     if not isinstance(t, torch.Tensor):
       t = torch.tensor(t, dtype=torch.float32)
-    out.append(t.to(device=dev, dtype=torch.float32))
+    _require_f32(t, "operand %d" % i)
+    out.append(t.to(device=dev))
   shape = torch.broadcast_shapes(*[t.shape for t in out])
   return out, shape
 
@@ -154,8 +164,8 @@ def circle_penalty(jx, jy, ox, oy, radius, inside_slope=1.0, outside_slope=0.1):
   dev = _device_for(jx, jy, ox, oy, radius)
   (a, b, c, d, e), _ = _prep(dev, jx, jy, ox, oy, radius)
   out = _CirclePenalty.apply(a, b, c, d, e, float(inside_slope), float(outside_slope))
-  if src.device != dev or src.dtype != torch.float32:
-    out = out.to(device=src.device, dtype=src.dtype if src.dtype.is_floating_point else torch.float32)
+  if src.device != dev:
+    out = out.to(device=src.device)
   return out
 
 
@@ -202,6 +212,6 @@ def joint_limit_penalty(theta, limit_min, limit_max, inside_slope=0.1, outside_s
   dev = _device_for(theta, limit_min, limit_max)
   (t, lo, hi), _ = _prep(dev, theta, limit_min, limit_max)
   out = _JointLimitPenalty.apply(t, lo, hi, float(inside_slope), float(outside_slope))
-  if src.device != dev or src.dtype != torch.float32:
-    out = out.to(device=src.device, dtype=src.dtype if src.dtype.is_floating_point else torch.float32)
+  if src.device != dev:
+    out = out.to(device=src.device)
   return out

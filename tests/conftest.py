@@ -8,8 +8,9 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "lagrange-dual-learning_b200")
+FUSED_OVERLAY = os.path.join(PKG, "fused_overlay")     # the fused trainer mirror (`scripts` package); see INTEGRATION.md
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-for p in (ROOT, PKG):
+for p in (ROOT, FUSED_OVERLAY, PKG):
   if p not in sys.path:
     sys.path.insert(0, p)
 

@@ -14,9 +14,18 @@ REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches")
 
 
-def test_reference_arm_prints_one_contract_line():
+HAVE_REF_TREE = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "scripts", "trainer.py"))
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_prints_one_contract_line(kind):
+  """kind "reference": the unmodified reference from baseline/_ref (tools/install_ref.py); "port": the oracle restatement,
+  which is what the arm falls back to when that tree is absent (forced here with --force-port)."""
+  if kind == "reference" and not HAVE_REF_TREE:
+    pytest.skip("baseline/_ref not installed")
   out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--cpu-batch-log2", "12"], capture_output=True, text=True, timeout=600)
+                        "--cpu-batch-log2", "12"] + (["--force-port"] if kind == "port" else []),
+                       capture_output=True, text=True, timeout=600)
   assert out.returncode == 0, out.stderr[-2000:]
   lines = [l for l in out.stdout.splitlines() if l.strip()]
   assert len(lines) == 1
@@ -25,7 +34,7 @@ def test_reference_arm_prints_one_contract_line():
     assert k in d, k
   assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
   assert d["metric"] == "fk_penalty_fwd_bwd_samples_per_s" and d["unit"] == "samples/s" and d["dtype"] == "f32" and d["vs_baseline"] is None
-  assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+  assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
   assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
   assert "workload" in d["config"] and d["gpu_launches"] == 0 and d["value"] > 0
 

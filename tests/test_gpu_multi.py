@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import GOLDEN, PKG, ROOT, config_json
+from conftest import FUSED_OVERLAY, GOLDEN, PKG, ROOT, config_json
 
 pytestmark = pytest.mark.gpu
 NAME = "cfg_joint_limits_and_4obs_dynamic"
@@ -27,7 +27,7 @@ def _build(tmpdir, tag):
 def _worker(rank, world, port, tmpdir):
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
-  for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+  for p in (ROOT, FUSED_OVERLAY, PKG, os.path.join(ROOT, "tests")):
     if p not in sys.path:
       sys.path.insert(0, p)
   torch.cuda.set_device(rank)

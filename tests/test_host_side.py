@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import GOLDEN, PKG, ROOT, config_json
+from conftest import FUSED_OVERLAY, GOLDEN, PKG, ROOT, config_json
 from oracle import ik_oracle as O
 
 REF = "/root/reference"
@@ -97,7 +97,7 @@ def test_shipped_multipliers_load_and_fit_the_constraint_layout():
 def _worker(rank, world, port, tmpdir):
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
-  for p in (ROOT, PKG):
+  for p in (ROOT, FUSED_OVERLAY, PKG):
     if p not in sys.path:
       sys.path.insert(0, p)
   dist.init_process_group("gloo", rank=rank, world_size=world)
