@@ -272,42 +272,188 @@ def run_reference(args):
   print(json.dumps(line))
 
 
+def multi_gpu_check(args, spec, dev, world, rank, lam, exchange):
+  """Correctness of the multi-GPU path, checked in the same run as the numbers (all ranks take part):
+    (1) the all-reduced sums are bit-identical on every rank;
+    (2) they equal the float64 sum of the ranks' local sums to <= 1e-5 of sum_r |partial_r| (north_star tolerance);
+    (3) three dual epochs (Adam steps + dual-ascent update) of the real trainer on device-resident data leave lambda and
+        the network weights bit-identical on every rank."""
+  import torch
+  import torch.distributed as dist
+  from ikl import fused, synthetic
+  K = spec.num_constraints
+  Bc = 1 << 20
+  theta, q_des, obst = synthetic.make_batch(Bc, seed=500 + rank, device=str(dev))
+  th, tg, ob = synthetic.to_planes(theta, q_des, obst)
+  local, _, _ = fused.lagrangian_forward_backward(spec, th, tg, ob, lam)
+  if exchange is not None:
+    glob, gloss, _ = fused.lagrangian_forward_backward(spec, th, tg, ob, lam, exchange=exchange)
+    glob = glob.clone()
+  else:
+    glob = local.clone()
+    dist.all_reduce(glob)
+  gathered = [torch.zeros_like(glob) for _ in range(world)]
+  dist.all_gather(gathered, glob)
+  sums_identical = all(torch.equal(g, gathered[0]) for g in gathered)
+  parts = [torch.zeros(K, dtype=torch.float64, device=dev) for _ in range(world)]
+  dist.all_gather(parts, local.double())
+  want = torch.stack(parts).sum(0)
+  scale = torch.stack(parts).abs().sum(0)
+  rel = float(((glob.double() - want).abs() / scale.clamp(min=1e-30)).max())
+  res = {"exchange": "in-kernel peer memory" if exchange is not None else "nccl all_reduce",
+         "sums_bit_identical_across_ranks": bool(sums_identical), "sums_max_rel_err_vs_f64_sum_of_partials": rel,
+         "sums_ok": bool(sums_identical and rel <= 1e-5)}
+  # (3) the trainer under torch.distributed
+  try:
+    import tempfile
+    sys.path.insert(0, os.path.join(PKG, "fused_overlay"))
+    from ikl.configs import write_config
+    from scripts.options import Options
+    from scripts.trainer import IkLagrangeDualTrainer
+    import contextlib
+    tmp = tempfile.mkdtemp(prefix="ikl_bench_multi_%d_" % rank)
+    cfg_path = write_config(__import__("ikl").standard_config(CONFIG_NAME), os.path.join(tmp, "cfg.json"))
+    opt = Options().parse(["--model_name", "check", "--config_file", cfg_path, "--log_dir", tmp, "--device_data", "--train_dataset_size", "65536",
+                           "--val_dataset_size", "16384", "--batch_size", "16384", "--lagrange_iters", "3", "--train_iters", "2",
+                           "--hidden_units", "32", "--initial_lambda", "1", "--penalty_good_slope", str(GOOD_SLOPE), "--model_save_hz", "1000"])
+    with contextlib.redirect_stdout(sys.stderr):
+      tr = IkLagrangeDualTrainer(opt)
+      for _ in range(3):
+        tr.train_with_relaxation(tr.lambda_multipliers)
+        tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
+    flat = torch.cat([tr.lambda_multipliers.reshape(-1)] + [p.detach().reshape(-1) for p in tr.model.parameters()])
+    flats = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(flats, flat)
+    res["trainer_lambda_and_weights_bit_identical_across_ranks"] = bool(all(torch.equal(f, flats[0]) for f in flats))
+    res["trainer_lambda_moved"] = bool((tr.lambda_multipliers != 1.0).any().item())
+  except Exception as e:
+    res["trainer_check_error"] = str(e)[:300]
+  res["ok"] = bool(res["sums_ok"] and res.get("trainer_lambda_and_weights_bit_identical_across_ranks", False))
+  return res
+
+
+def strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms_full):
+  """north_star config 5 as written: ONE batch of 2^24 samples sharded over the N ranks (2^24 / N each), fwd+bwd + the
+  all-reduce of the 16 sums every step.  At 2^21 samples per rank the kernel lasts ~27 us -- the order of a kernel launch
+  from Python and of a small NCCL all-reduce -- so the steps are captured in a CUDA graph (no host in the loop) and the
+  exchange happens inside the kernel over peer memory.  Device time, max over ranks."""
+  import torch
+  import torch.distributed as dist
+  from ikl import fused, synthetic
+  total = 1 << args.strong_total_log2
+  Bs = total // world
+  K = spec.num_constraints
+  theta, q_des, obst = synthetic.make_batch(Bs, seed=7000 + rank, device=str(dev))
+  th, tg, ob = synthetic.to_planes(theta, q_des, obst)
+  del theta, q_des, obst
+  dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
+  out = torch.empty(K + 1, dtype=torch.float32, device=dev)
+  S = 50                                   # steps per graph replay
+
+  def timed_graph(body, reps=10):
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      for _ in range(3):
+        body()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=side):
+        for _ in range(S):
+          body()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g.replay()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / (reps * S)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  local_ms = timed_graph(lambda: fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out))
+  res = {"total_batch": total, "batch_per_gpu": Bs, "steps_per_graph_replay": S, "kernel_only_ms": local_ms}
+  if world == 1:
+    step_ms = local_ms
+    res["exchange"] = "none (single GPU)"
+  elif exchange is not None:
+    step_ms = timed_graph(lambda: fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out, exchange=exchange))
+    res["exchange"] = "inside the fused kernel: NVLink peer stores of the 16 fp64 sums + flag, last block pulls and adds"
+  else:
+    def body():
+      fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out)
+      dist.all_reduce(out)
+    step_ms = timed_graph(body)
+    res["exchange"] = "NCCL all_reduce of 17 floats after each kernel (captured in the graph)"
+  if world > 1 and exchange is not None and args.compare_nccl:
+    def body_nccl():
+      fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out)
+      dist.all_reduce(out)
+    res["nccl_variant_ms_per_step"] = timed_graph(body_nccl)
+  ideal = kernel_ms_full * (total / float(1 << args.batch_log2)) / world
+  res.update({"ms_per_step": step_ms, "samples_per_s": total / (step_ms * 1e-3), "exchange_overhead_us": (step_ms - local_ms) * 1e3,
+              "ideal_ms": ideal, "efficiency_vs_ideal": ideal / step_ms,
+              "frac_of_hbm_peak": ALGO_BYTES_PER_SAMPLE * Bs / (step_ms * 1e-3) / 1e9 / measured_peak()[0],
+              "limiter": "fixed per-launch cost (grid ramp-up, tail, final reduction: kernel_only_ms vs ideal_ms) "
+                         "and the in-kernel exchange (exchange_overhead_us); no host or NCCL launch in the loop"})
+  return res
+
+
 def train_step_metric(args, spec, dev, world, lam):
-  """Secondary metric of BASELINE.json: full dual-learning train steps/s -- SimpleNetwork (H=100, depth 8, dropout 0.05,
-  83 203 parameters; cuBLAS) forward, the fused Lagrangian kernel, backward through the network, one flat all-reduce of
-  [gradients | 16 violation sums] when N > 1, Adam (lr 5e-5).  Synthetic on-device batches of 2^20 samples per GPU."""
+  """Secondary metric of BASELINE.json on the configuration SURVEY 8(d) names: full dual-learning train steps/s with 2^24
+  samples per step over ALL ranks (2^24 / N per rank: strong scaling), micro-batched.  Per micro-batch: SimpleNetwork (H=100,
+  depth 8, dropout 0.05, 83 203 parameters; cuBLAS) forward with the last layer transposed so theta comes out as planes,
+  the fused TMA-staged Lagrangian kernel (sums + d/dtheta in one pass, no gradient rescaling pass), backward through the
+  network accumulating into .grad; per step ONE flat all-reduce of [gradients | 16 violation sums] when N > 1, then Adam
+  (lr 5e-5).  Synthetic on-device data.  The step is bounded by the network, which north_star keeps on cuBLAS:
+  `fused_kernel_share` says how little of it is the hot path of this repo."""
   import torch
   import torch.distributed as dist
   from ikl import dist as ikl_dist, fused, synthetic
   from models.simple_network import SimpleNetwork
-  B = 1 << args.train_batch_log2
+  rank = int(os.environ.get("RANK", "0"))
+  total = 1 << args.train_total_log2
+  per_rank = total // world
+  micro = min(1 << args.train_micro_log2, per_rank)
+  n_micro = per_rank // micro
   torch.manual_seed(1234)
   model = SimpleNetwork(20, 3, hidden_units=100, depth=8, dropout=0.05).to(dev)
   ikl_dist.broadcast_parameters(model)
   opt = torch.optim.Adam(model.parameters(), lr=5e-5, betas=(0.9, 0.999))
-  rank = int(os.environ.get("RANK", "0"))
-  theta0, q_des, obst = synthetic.make_batch(B, seed=1000 + rank, device=str(dev))
-  x = torch.zeros(B, 20, device=dev)                 # kinematics/dataset.py:124-153 input template
+  theta0, q_des, obst = synthetic.make_batch(per_rank, seed=1000 + rank, device=str(dev))
+  x = torch.zeros(per_rank, 20, device=dev)                 # kinematics/dataset.py:124-153 input template
   x[:, 0:2] = q_des[:, :2]
   x[:, 2], x[:, 3] = -synthetic.LIMIT, synthetic.LIMIT
-  x[:, 4:] = obst.reshape(B, 16)
+  x[:, 4:] = obst.reshape(per_rank, 16)
+  _, q_pl, ob_pl = synthetic.to_planes(theta0, q_des, obst)
+  del theta0, q_des, obst
   lam_dev = torch.tensor(lam, device=dev)
+  viol_sum = torch.zeros(spec.num_constraints, device=dev)
 
   def step():
-    theta = model(x)
-    viol, loss = fused.FusedIkLagrangian.apply(theta, q_des, obst, lam_dev, spec, lam)
     model.zero_grad()
-    loss.backward()
-    ikl_dist.all_reduce_gradients(model, extra=viol)
+    viol_sum.zero_()
+    for m in range(n_micro):
+      sl = slice(m * micro, (m + 1) * micro)
+      theta = model.forward_planes(x[sl])
+      viol, loss = fused.FusedIkLagrangian.apply(theta, q_pl[sl], ob_pl[sl], lam_dev, spec, lam, True)
+      loss.backward()                                   # gradients of the sums add up over the micro-batches
+      viol_sum.add_(viol.detach())
+    ikl_dist.all_reduce_gradients(model, extra=viol_sum)
     opt.step()
 
-  for _ in range(3):
+  for _ in range(2):
     step()
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  n = max(3, min(args.steps, 10))
+  n = max(2, min(args.steps, 4))
   e0.record()
   for _ in range(n):
     step()
@@ -317,9 +463,25 @@ def train_step_metric(args, spec, dev, world, lam):
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms = float(t.item())
-  return {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "samples_per_s": world * B / (ms * 1e-3), "batch_per_gpu": B, "steps": n,
-          "model": "SimpleNetwork(20->100x8->3, dropout 0.05, 83203 params) on cuBLAS + fused IK Lagrangian + Adam",
-          "exchange": "one flat all-reduce of [83203 gradients | 16 violation sums]" if world > 1 else "none"}
+  # the fused kernel alone on one micro-batch of the same tensors
+  with torch.no_grad():
+    th = model.forward_planes(x[:micro]).detach()
+  dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
+  for _ in range(3):
+    fused.lagrangian_forward_backward(spec, th, q_pl[:micro], ob_pl[:micro], lam, dtheta=dth)
+  k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  k0.record()
+  for _ in range(20):
+    fused.lagrangian_forward_backward(spec, th, q_pl[:micro], ob_pl[:micro], lam, dtheta=dth)
+  k1.record()
+  torch.cuda.synchronize()
+  kernel_ms = k0.elapsed_time(k1) / 20
+  return {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "samples_per_s": total / (ms * 1e-3), "samples_per_step": total,
+          "batch_per_gpu": per_rank, "micro_batch": micro, "micro_batches_per_step": n_micro, "steps": n, "scaling": "strong",
+          "fused_kernel_ms_per_micro_batch": kernel_ms, "fused_kernel_share": kernel_ms * n_micro / ms,
+          "model": "SimpleNetwork(20->100x8->3, dropout 0.05, 83203 params) on cuBLAS + fused IK Lagrangian (planes, TMA) + Adam",
+          "note": "bounded by the fp32 cuBLAS network (out of scope per north_star); the hot path of this repo is fused_kernel_share of the step",
+          "exchange": "one flat all-reduce of [83203 gradients | 16 violation sums] per step" if world > 1 else "none"}
 
 
 def small_batch_train_metric(args, spec, dev, lam):
@@ -417,6 +579,21 @@ def run_ours(args):
     # 64-byte all-reduce overlaps the next step's kernel either way: profiles/r01/bench_n2_*.json)
     _cabi.set_reserved_sms(args.reserve_sms)
 
+  # The K sums are all-reduced INSIDE the fused kernel over NVLink peer memory (ikl.exchange.PeerExchange, include/ikl.h
+  # IklExchange); --exchange nccl keeps the round-1 form (one asynchronous 64-byte NCCL all-reduce per step) for comparison.
+  exchange, exchange_note = None, None
+  if world > 1 and args.exchange == "peer":
+    ok = torch.ones(1, device=dev)
+    try:
+      from ikl.exchange import PeerExchange
+      exchange = PeerExchange(device=dev)
+    except Exception as e:
+      ok.zero_()
+      exchange_note = "peer exchange unavailable on this rank (%s)" % (str(e)[:160],)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+      exchange, exchange_note = None, exchange_note or "peer exchange unavailable on another rank"
+
   spec = ConstraintSpec.from_config(standard_config(CONFIG_NAME), 3, GOOD_SLOPE, BAD_SLOPE)
   K = spec.num_constraints
   B = 1 << args.batch_log2
@@ -433,6 +610,9 @@ def run_ours(args):
   pending = []
 
   def step():
+    if exchange is not None:          # ONE kernel: compute + all-reduce of the 16 sums over peer memory; viol is global
+      viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta, exchange=exchange)
+      return viol, loss
     viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta)
     if world > 1:
       # 16 floats: every rank sees the global sums that drive the multiplier update.  Asynchronous: NCCL's stream
@@ -515,7 +695,9 @@ def run_ours(args):
         "config": {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
                    "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
                    "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
-                   "parallelism": "batch shard per GPU; asynchronous all-reduce of the 16 violation sums per step (overlaps the next step's kernel)" if world > 1 else "single GPU"},
+                   "parallelism": ("single GPU" if world == 1 else
+                                   "batch shard per GPU; the 16 violation sums all-reduced inside the fused kernel over NVLink peer memory" if exchange is not None else
+                                   "batch shard per GPU; asynchronous NCCL all-reduce of the 16 violation sums per step (overlaps the next step's kernel)")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
                      "peak_source": peak_src},
@@ -594,6 +776,15 @@ def run_ours(args):
            "api": "ikl.host_pipeline.HostLagrangianPipeline.run (pinned host rows-layout tensors in, host dtheta + sums out)",
            "numa_bind": numa}
 
+  multi_check = None
+  if world > 1 and not args.skip_multi_check:
+    multi_check = multi_gpu_check(args, spec, dev, world, rank, lam, exchange)
+    if exchange_note:
+      multi_check["exchange_note"] = exchange_note
+  strong = None
+  if not args.skip_strong:
+    strong = strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms_full=kernel_ms)
+
   train = None
   if not args.skip_train_step:
     train = train_step_metric(args, spec, dev, world, lam)
@@ -605,6 +796,8 @@ def run_ours(args):
   if rank == 0:
     line["e2e"] = e2e
     line["train_step"] = train
+    line["multi_gpu_check"] = multi_check
+    line["strong_scaling"] = strong
     line["train_step_batch8"] = small
     line["context"] = extras
     if not args.skip_cpu and world == 1:
@@ -629,13 +822,20 @@ def main():
   ap.add_argument("--e2e-batch-log2", type=int, default=24)
   ap.add_argument("--e2e-chunk-log2", type=int, default=21)
   ap.add_argument("--cpu-batch-log2", type=int, default=21)
-  ap.add_argument("--train-batch-log2", type=int, default=20)
   ap.add_argument("--skip-train-step", action="store_true")
   ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1 only: SMs left out of the persistent grid for the concurrent NCCL kernel")
   ap.add_argument("--no-numa-bind", action="store_true")
   ap.add_argument("--skip-context", action="store_true")
   ap.add_argument("--skip-e2e", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
+  ap.add_argument("--skip-multi-check", action="store_true")
+  ap.add_argument("--skip-strong", action="store_true")
+  ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                  help="N > 1: how the 16 sums are all-reduced (peer = inside the fused kernel over NVLink peer memory)")
+  ap.add_argument("--strong-total-log2", type=int, default=24, help="total batch of the strong-scaling measurement (sharded over the ranks)")
+  ap.add_argument("--compare-nccl", action="store_true", help="strong scaling: also time kernel + NCCL all-reduce in a CUDA graph")
+  ap.add_argument("--train-total-log2", type=int, default=24, help="samples per train step over ALL ranks (SURVEY 8d), micro-batched")
+  ap.add_argument("--train-micro-log2", type=int, default=20, help="micro-batch per GPU inside a train step")
   ap.add_argument("--force-port", action="store_true", help="--impl reference: time the oracle port even when baseline/_ref is installed")
   args = ap.parse_args()
   if args.impl == "reference":

@@ -35,10 +35,11 @@
 extern "C" {
 #endif
 
-#define IKL_ABI_VERSION 2
+#define IKL_ABI_VERSION 3
 #define IKL_MAX_LINKS 3        /* reference trainer supports 3 (scripts/trainer.py:177-180); 2 is templated too */
 #define IKL_MAX_OBSTACLES 4    /* reference hard-wires (B,4,4): scripts/trainer.py:218, kinematics/dataset.py:80 */
 #define IKL_MAX_CONSTRAINTS (1 + IKL_MAX_LINKS + IKL_MAX_LINKS * IKL_MAX_OBSTACLES)   /* 16 */
+#define IKL_MAX_RANKS 8        /* GPUs of one NVSwitch box that can take part in the in-kernel exchange of the K sums */
 
 typedef enum IklStatus {
   IKL_OK = 0,
@@ -124,6 +125,35 @@ IklStatus ikl_lagrangian_forward(const IklSpec* spec, const IklBatch* in, const 
 IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w,
                                           void* workspace, float* viol_out, float* loss_out, double* viol_accum,
                                           float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj, void* stream);
+
+/* ---- multi-GPU: the K sums exchanged INSIDE the kernel over NVLink peer memory ---------------------------------------
+ * The reference has no distributed code; the path shards because every constraint value is a SUM over samples
+ * (scripts/trainer.py:195,204,239).  With one process per GPU, each rank runs the fused kernel on its shard; the block that
+ * finishes a rank's reduction stores that rank's K double-precision sums straight into every peer's mailbox (NVLink P2P
+ * stores), raises a flag there (release, system scope), waits for the K-vectors of all peers to land in its own mailbox
+ * and adds them in rank order -- so viol_out / loss_out / viol_accum hold the GLOBAL sums, bit-identical on every rank,
+ * when the launch completes.  One kernel does the compute and the collective: no NCCL launch, no second kernel.
+ *   peers[r]  rank r's exchange buffer (ikl_exchange_bytes() bytes, zero-filled once by its owner before anyone's first
+ *             launch) as mapped into THIS process -- CUDA IPC / symmetric memory; peers[rank] is the local buffer.
+ * Every rank must issue the same sequence of *_allreduce launches (they pair up by a sequence counter kept in the local
+ * buffer, so CUDA-graph replays work); a peer that never arrives makes the kernel trap after a few seconds instead of
+ * hanging the GPU. */
+typedef struct IklExchange {
+  int32_t rank, world;            /* 0 <= rank < world <= IKL_MAX_RANKS */
+  void* peers[IKL_MAX_RANKS];
+} IklExchange;
+
+size_t ikl_exchange_bytes(void);
+
+/* ikl_lagrangian_forward / ikl_lagrangian_forward_backward on this rank's shard, sums exchanged as described above.
+ * dtheta is local to the shard (the gradient of the GLOBAL Lagrangian w.r.t. this rank's samples). */
+IklStatus ikl_lagrangian_forward_allreduce(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
+                                           float* viol_out, float* loss_out, double* viol_accum, const IklExchange* ex,
+                                           void* stream);
+IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const IklBatch* in, const IklWeights* w,
+                                                    void* workspace, float* viol_out, float* loss_out, double* viol_accum,
+                                                    float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
+                                                    const IklExchange* ex, void* stream);
 
 /* Backward alone: d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights w (for autograd:
  * w_i = grad(lagrange_loss) * lambda_i + grad(constraint_violations)_i).  Recomputes from the inputs -- nothing is

@@ -235,10 +235,15 @@ namespace {
 
 IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
               double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
-              void* stream) {
+              void* stream, const IklExchange* ex = nullptr) {
   IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
   if (st != IKL_OK) return st;
   if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
+  if (ex) {
+    if (ex->world < 1 || ex->world > IKL_MAX_RANKS || ex->rank < 0 || ex->rank >= ex->world) return IKL_ERR_INVALID_ARGUMENT;
+    for (int r = 0; r < ex->world; ++r)
+      if (!ex->peers[r] || (reinterpret_cast<uintptr_t>(ex->peers[r]) & 15u)) return IKL_ERR_INVALID_ARGUMENT;
+  }
 
   LagrangianParams p;
   Variant v;
@@ -253,6 +258,11 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   p.viol_out = viol_out;
   p.loss_out = loss_out;
   p.viol_accum = viol_accum;
+  if (ex && ex->world > 1) {
+    p.ex_world = ex->world;
+    p.ex_rank = ex->rank;
+    for (int r = 0; r < ex->world; ++r) p.ex_peer[r] = reinterpret_cast<ExchangeBuf*>(ex->peers[r]);
+  }
 
   const int forced = forced_layout();
   cudaStream_t cs = (cudaStream_t)stream;
@@ -295,6 +305,21 @@ IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* i
                                           float* loss_out, double* viol_accum, float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
                                           void* stream) {
   return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream);
+}
+
+size_t ikl_exchange_bytes(void) { return sizeof(ExchangeBuf); }
+
+IklStatus ikl_lagrangian_forward_allreduce(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out,
+                                           float* loss_out, double* viol_accum, const IklExchange* ex, void* stream) {
+  if (!ex) return IKL_ERR_INVALID_ARGUMENT;
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, nullptr, 0, 0, false, stream, ex);
+}
+
+IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
+                                                    float* viol_out, float* loss_out, double* viol_accum, float* dtheta,
+                                                    int64_t dtheta_sb, int64_t dtheta_sj, const IklExchange* ex, void* stream) {
+  if (!ex) return IKL_ERR_INVALID_ARGUMENT;
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream, ex);
 }
 
 IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* dtheta,

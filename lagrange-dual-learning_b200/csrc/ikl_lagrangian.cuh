@@ -51,6 +51,17 @@ enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
 
 struct alignas(64) TensorMap { unsigned long long opaque[16]; };      // same size and alignment as the driver's CUtensorMap
 
+// One rank's mailbox for the in-kernel exchange of the K sums (include/ikl.h: IklExchange).  mail[parity][r] receives rank
+// r's K-vector of the launch with sequence number seq (parity = seq & 1), flag[parity][r] the sequence number once it has
+// landed.  Two parities suffice: a rank can only be one launch ahead of a peer, because finishing launch s needs every
+// peer's flag of launch s.  `seq` is the owner's private launch counter (device-side, so graph replays advance it).
+constexpr int kMaxRanks = IKL_MAX_RANKS;
+struct ExchangeBuf {
+  double mail[2][kMaxRanks][kMaxK];
+  unsigned long long flag[2][kMaxRanks];
+  unsigned long long seq;
+};
+
 struct LagrangianParams {
   Uniforms u;
   PackedUniforms pu;
@@ -75,6 +86,9 @@ struct LagrangianParams {
   float stats_threshold;
   unsigned long long* stats_counts;
   double* stats_pos_err;
+  // in-kernel all-reduce of the K sums over peer memory (ex_world <= 1: off)
+  int ex_world, ex_rank;
+  ExchangeBuf* ex_peer[kMaxRanks];
 };
 static_assert(sizeof(LagrangianParams) <= 4096, "kernel parameter block too large");
 
@@ -123,6 +137,60 @@ struct SharedAcc {
   }
 };
 
+// ---- in-kernel all-reduce over NVLink peer memory (IklExchange) ---------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by the whole LAST block of a rank's launch; thread i < K passes this rank's total of constraint i and gets the
+// global one back.  Push: thread i stores its total into slot [parity][rank][i] of EVERY rank's mailbox (its own included),
+// fences to system scope, the block meets, and thread r < world raises flag[parity][rank] in rank r's mailbox with a
+// release store.  Pull: thread r < world spins (acquire loads) on its own mailbox's flag[parity][r] until rank r's launch
+// with the same sequence number has pushed; the block meets again and thread i adds the K-vectors in rank order -- the same
+// order of the same doubles on every rank, hence bit-identical results.  A peer that never shows up trips the poll limit
+// (seconds) and the kernel traps rather than hanging.
+template <int K>
+__device__ __forceinline__ double exchange_sums(const LagrangianParams& p, double mine) {
+  const int tid = threadIdx.x;
+  ExchangeBuf* own = p.ex_peer[p.ex_rank];
+  const unsigned long long seq = own->seq + 1;      // only this block (the last one) of this rank touches own->seq
+  const int par = (int)(seq & 1ull);
+  if (tid < K) {
+    for (int r = 0; r < p.ex_world; ++r) st_relaxed_sys_f64(&p.ex_peer[r]->mail[par][p.ex_rank][tid], mine);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < p.ex_world) {
+    st_release_sys(&p.ex_peer[tid]->flag[par][p.ex_rank], seq);
+    unsigned long long polls = 0;
+    while (ld_acquire_sys(&own->flag[par][tid]) < seq) {
+      __nanosleep(64);
+      if (++polls > (1ull << 26)) asm volatile("trap;");
+    }
+  }
+  __syncthreads();
+  double tot = 0.0;
+  if (tid < K) {
+    for (int r = 0; r < p.ex_world; ++r) tot += ld_relaxed_sys_f64(&own->mail[par][r][tid]);
+  }
+  __syncthreads();
+  if (tid == 0) own->seq = seq;
+  return tot;
+}
+
 // Block-level tail shared by every kernel: s_red[warp][i] holds each warp's fp64 sum of constraint i.
 template <int K>
 __device__ __forceinline__ void block_finalize(const LagrangianParams& p, double (*s_red)[kMaxK]) {
@@ -150,10 +218,13 @@ __device__ __forceinline__ void block_finalize(const LagrangianParams& p, double
     s_fin[part][i] = v;
   }
   __syncthreads();
+  double tot = 0.0;
   if (tid < K) {
-    double tot = 0.0;
 #pragma unroll
     for (int part = 0; part < kFinalParts; ++part) tot += s_fin[part][tid];
+  }
+  if (p.ex_world > 1) tot = exchange_sums<K>(p, tot);       // block-uniform branch; contains block barriers
+  if (tid < K) {
     p.viol_out[tid] = (float)tot;
     if (p.viol_accum) p.viol_accum[tid] += tot;
     const float wi = (p.w_dev != nullptr) ? p.w_dev[tid] : p.u.w[tid];

@@ -10,8 +10,9 @@ log-directory contents and checkpoint layout.  What changes underneath:
     function-level CUDA drop-ins (kinematics.forward_kinematics / kinematics.penalties).
   * update_multipliers keeps the running sum of the per-batch K-vectors on the device in float64 and applies
     lambda <- max(0, lambda + lr * sum) with ikl_dual_update (trainer.py:274-284).
-  * With torch.distributed initialised (torchrun), every rank processes its shard of each batch; the model gradients and
-    the K violation sums travel in ONE flat all-reduce (ikl.dist), so lambda and the weights stay identical on all ranks.
+  * With torch.distributed initialised (torchrun), every rank processes its shard of each batch; the model gradients
+    travel in ONE flat all-reduce per step and the K violation sums of the dual step in one all-reduce of K doubles
+    (ikl.dist), so lambda and the weights stay identical on all ranks.
 
 The network itself (models.simple_network.SimpleNetwork) stays on PyTorch / cuBLAS.
 """
@@ -66,23 +67,52 @@ def _git_sha():
 
 class BatchOutputs(dict):
   """The `outputs` dict of process_batch.  Entries the training loop never reads (q_ee_actual, position_err_sq,
-  joint_angle_l2) are materialised on first access so the fused kernel does not have to write them every step."""
+  joint_angle_l2) are materialised on first access so the fused kernel does not have to write them every step.  Every way
+  of reading a plain dict sees them: indexing, get(), `in`, keys(), iteration, len(), items(), values(), dict(outputs)."""
 
   def __init__(self, lazy):
     super(BatchOutputs, self).__init__()
     self._lazy = lazy
 
+  def _materialise(self, key=None):
+    for k in ([key] if key is not None else list(self._lazy.keys())):
+      if k in self._lazy:                    # one thunk may fill several entries (q_ee_actual and position_err_sq)
+        self._lazy.pop(k)(self)
+
   def __missing__(self, key):
     if key in self._lazy:
-      self._lazy.pop(key)(self)
+      self._materialise(key)
       return dict.__getitem__(self, key)
     raise KeyError(key)
+
+  def get(self, key, default=None):
+    if key in self._lazy:
+      self._materialise(key)
+    return dict.get(self, key, default)
 
   def __contains__(self, key):
     return dict.__contains__(self, key) or key in self._lazy
 
+  def __len__(self):
+    return dict.__len__(self) + len(self._lazy)
+
   def keys(self):
     return list(dict.keys(self)) + list(self._lazy.keys())
+
+  def __iter__(self):
+    return iter(self.keys())
+
+  def items(self):
+    self._materialise()
+    return dict.items(self)
+
+  def values(self):
+    self._materialise()
+    return dict.values(self)
+
+  def copy(self):
+    self._materialise()
+    return dict(dict.items(self))
 
 
 class IkLagrangeDualTrainer(object):
@@ -102,7 +132,11 @@ class IkLagrangeDualTrainer(object):
     self.device = torch.device(device if device != "cuda" else "cuda:%d" % torch.cuda.current_device())
     self.model = SimpleNetwork(20, self.opt.num_links, hidden_units=self.opt.hidden_units, depth=8, dropout=0.05).to(self.device)
     ikl_dist.broadcast_parameters(self.model)
-    self.use_graph = bool(getattr(self.opt, "cuda_graph", False)) and self.world == 1 and self.device.type == "cuda"
+    self.use_graph = bool(getattr(self.opt, "cuda_graph", False)) and self.device.type == "cuda"
+    if self.use_graph and self.opt.batch_size % self.world != 0:
+      print("NOTE: --cuda_graph needs --batch_size divisible by the world size (every rank replays the same graph); running eagerly")
+      self.use_graph = False
+    self._unit_upstream = False
     self.optimizer = Adam(self.model.parameters(), lr=self.opt.optimizer_lr, betas=(0.9, 0.999), capturable=self.use_graph)
     self._graph_step = None
 
@@ -216,7 +250,7 @@ class IkLagrangeDualTrainer(object):
     outputs = BatchOutputs({"q_ee_actual": side_outputs, "position_err_sq": side_outputs, "joint_angle_l2": angle_l2})
     outputs["pred_joint_theta"] = pred_joint_theta
     viol, loss = fused.FusedIkLagrangian.apply(pred_joint_theta, q_ee_desired, obstacles, lamda, spec,
-                                               self._host_multipliers(lamda))
+                                               self._host_multipliers(lamda), self._unit_upstream)
     outputs["constraint_violations"] = viol
     outputs["lagrange_loss"] = loss
     return outputs
@@ -263,22 +297,28 @@ class IkLagrangeDualTrainer(object):
   # ---------------------------------------------------------------------------------------------------------------
   def train_with_relaxation(self, lamda):
     """One epoch of Adam steps on the Lagrangian relaxation with the multipliers held fixed (trainer.py:251-265)."""
-    sampler = getattr(self.train_loader, "sampler", None)
-    if hasattr(sampler, "set_epoch"):           # DistributedSampler: a new permutation every relaxation epoch
+    sampler = getattr(self.train_loader, "batch_sampler", None)
+    if hasattr(sampler, "set_epoch"):           # ShardedBatchSampler: a new permutation every relaxation epoch
       self._relaxation_epoch = getattr(self, "_relaxation_epoch", -1) + 1
       sampler.set_epoch(self._relaxation_epoch)
     if self.use_graph and self._graph_step is None:
       from ikl.graph_step import GraphedTrainStep
-      self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size, self.device)
+      self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size // self.world, self.device,
+                                          planes=bool(getattr(self.opt, "device_data", False)))
     if self._graph_step is not None:
       self._graph_step.set_multipliers(lamda)
     for ti, inputs in enumerate(self.train_loader):
       if ti >= self.opt.train_iters:
         break
-      if self._graph_step is not None and len(inputs["q_ee_desired"]) == self.opt.batch_size:
-        self._graph_step.step(inputs)          # the whole step (forward, Lagrangian, backward, Adam) is one graph replay
+      # a global batch of exactly batch_size samples deals batch_size / world to every rank: all ranks take the same branch
+      if self._graph_step is not None and len(inputs["q_ee_desired"]) == self._graph_step.batch_size:
+        self._graph_step.step(inputs)          # the whole step (forward, Lagrangian, backward, all-reduce, Adam) is one graph replay
         continue
-      outputs = self.process_batch(inputs, lamda)
+      self._unit_upstream = True               # .backward() below starts at the Lagrangian itself: no gradient rescaling pass
+      try:
+        outputs = self.process_batch(inputs, lamda)
+      finally:
+        self._unit_upstream = False
       self.model.zero_grad()
       outputs["lagrange_loss"].backward()
       ikl_dist.all_reduce_gradients(self.model)
@@ -312,12 +352,23 @@ class IkLagrangeDualTrainer(object):
     supervised = torch.zeros(n)
     violations = torch.zeros(n, len(lamda))
     lagrange = torch.zeros(n)
+    counts = torch.zeros(n)
     with torch.no_grad():
       for vi, inputs in enumerate(self.val_loader):
         outputs = self.process_batch(inputs, lamda)
-        supervised[vi] = outputs["joint_angle_l2"]
+        counts[vi] = len(inputs["q_ee_desired"])
+        supervised[vi] = outputs["joint_angle_l2"] if counts[vi] > 0 else 0.0
         violations[vi, :] = outputs["constraint_violations"]
         lagrange[vi] = outputs["lagrange_loss"]
+    if self.world > 1:
+      # every rank saw its share of each validation batch: batch sums add up, the per-batch mean of theta^2 is a weighted mean
+      pack = torch.cat([violations.reshape(-1), lagrange, supervised * counts, counts]).to(self.device)
+      ikl_dist.all_reduce_sum(pack)
+      pack = pack.cpu()
+      k = violations.numel()
+      violations = pack[:k].view_as(violations)
+      lagrange, weighted, counts = pack[k:k + n], pack[k + n:k + 2 * n], pack[k + 2 * n:]
+      supervised = weighted / counts.clamp(min=1)
     mean_violation = violations.mean(axis=0)
     if self.rank == 0:
       print("==> Epoch {} (Train Time = {:.3f} sec, Mult Time = {:.3f} sec)\n  Orig Loss={}\n  Constraints={}\n  Lagrange Loss={}\n  Multipliers={}".format(

@@ -15,7 +15,8 @@ _c_vp = ctypes.c_void_p
 MAX_LINKS = 3
 MAX_OBSTACLES = 4
 MAX_CONSTRAINTS = 1 + MAX_LINKS + MAX_LINKS * MAX_OBSTACLES
-ABI_VERSION = 2
+MAX_RANKS = 8
+ABI_VERSION = 3
 
 IKL_OK, IKL_ERR_INVALID_ARGUMENT, IKL_ERR_UNSUPPORTED, IKL_ERR_CUDA = 0, 1, 2, 3
 
@@ -42,6 +43,10 @@ class IklWeights(ctypes.Structure):
   _fields_ = [("host", ctypes.POINTER(_c_f)), ("device", _c_vp)]
 
 
+class IklExchange(ctypes.Structure):
+  _fields_ = [("rank", _c_i32), ("world", _c_i32), ("peers", _c_vp * MAX_RANKS)]
+
+
 # name -> (restype, argtypes); mirrors include/ikl.h one to one (tests/test_cabi_symbols.py parses the header)
 _SIGNATURES = {
     "ikl_num_constraints": (_c_i32, [ctypes.POINTER(IklSpec)]),
@@ -50,6 +55,12 @@ _SIGNATURES = {
                                               _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "ikl_lagrangian_forward_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
                                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
+    "ikl_exchange_bytes": (ctypes.c_size_t, []),
+    "ikl_lagrangian_forward_allreduce": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
+                                                        _c_vp, _c_vp, _c_vp, _c_vp, ctypes.POINTER(IklExchange), _c_vp]),
+    "ikl_lagrangian_forward_backward_allreduce": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch),
+                                                                 ctypes.POINTER(IklWeights), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                                                 _c_i64, ctypes.POINTER(IklExchange), _c_vp]),
     "ikl_lagrangian_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
                                                _c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "ikl_dual_update": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_i32, _c_vp, _c_vp]),

@@ -9,6 +9,7 @@ PyTorch is used for device memory and streams only; all arithmetic happens in li
 reached through the C ABI in include/ikl.h.  There is no CPU fallback: CPU tensors raise.
 """
 import ctypes
+import os
 
 import torch
 
@@ -100,12 +101,14 @@ def _check_accum(viol_accum, K, device):
 
 
 def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, want_q_ee=False,
-                       want_err_sq=False):
+                       want_err_sq=False, exchange=None):
   """Constraint sums and Lagrangian of one batch, forward only.
 
   Returns a dict with the reference's output keys: constraint_violations (K,), lagrange_loss (),
   and optionally q_ee_actual (B,3), position_err_sq (B,2)   (scripts/trainer.py:184,193,244,247).
   ``viol_accum`` (K float64 on device) is incremented by the sums: the running total update_multipliers needs.
+  ``exchange`` (ikl.exchange.PeerExchange): this call is one rank's shard; the sums are all-reduced inside the kernel over
+  NVLink peer memory and every output holds the GLOBAL value (side outputs are not available in that mode).
   """
   lib = _cabi.load()
   K = spec.num_constraints
@@ -117,11 +120,19 @@ def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol
     B = theta.shape[0]
     q_ee = torch.empty(B, 3, dtype=torch.float32, device=dev) if want_q_ee else None
     err = torch.empty(B, 2, dtype=torch.float32, device=dev) if want_err_sq else None
-    st = lib.ikl_lagrangian_forward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
-                                    ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                    ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
-                                    ctypes.c_void_p(q_ee.data_ptr()) if want_q_ee else None,
-                                    ctypes.c_void_p(err.data_ptr()) if want_err_sq else None, _stream_ptr(dev))
+    if exchange is not None:
+      if want_q_ee or want_err_sq:
+        raise ValueError("side outputs are per-shard; request them from a call without exchange=")
+      st = lib.ikl_lagrangian_forward_allreduce(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                                ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+                                                exchange.byref(), _stream_ptr(dev))
+    else:
+      st = lib.ikl_lagrangian_forward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                      ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                      ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+                                      ctypes.c_void_p(q_ee.data_ptr()) if want_q_ee else None,
+                                      ctypes.c_void_p(err.data_ptr()) if want_err_sq else None, _stream_ptr(dev))
   _cabi.check(st, "ikl_lagrangian_forward")
   res = {"constraint_violations": out[:K], "lagrange_loss": out[K]}
   if want_q_ee:
@@ -131,8 +142,11 @@ def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol
   return res
 
 
-def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, dtheta=None):
-  """One pass: (constraint_violations (K,), lagrange_loss (), dtheta (B,J)) with dtheta = d(sum_i lam_i g_i)/d(theta)."""
+def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, dtheta=None, exchange=None,
+                                out=None):
+  """One pass: (constraint_violations (K,), lagrange_loss (), dtheta (B,J)) with dtheta = d(sum_i lam_i g_i)/d(theta).
+  With ``exchange`` (ikl.exchange.PeerExchange) the call is one rank's shard and the sums / loss are the GLOBAL ones,
+  all-reduced inside the kernel over NVLink peer memory.  ``out``: optional (K+1,) float32 buffer for [sums | loss]."""
   lib = _cabi.load()
   K = spec.num_constraints
   if lam is None:
@@ -141,7 +155,8 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
   dev = theta.device
   w = _Weights(lam, K, dev)
   with torch.cuda.device(dev):
-    out = torch.empty(K + 1, dtype=torch.float32, device=dev)
+    if out is None:
+      out = torch.empty(K + 1, dtype=torch.float32, device=dev)
     if dtheta is None:
       # planes in (theta.stride(0) == 1, possibly a slice of wider planes) -> planes out; otherwise row-major
       if theta.dim() == 2 and theta.shape[0] > 1 and theta.stride(0) == 1:
@@ -152,11 +167,13 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
       _require_cuda_f32(dtheta, "dtheta")
       if dtheta.shape != theta.shape:
         raise ValueError("dtheta must have theta's shape")
-    st = lib.ikl_lagrangian_forward_backward(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
-                                             ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                             ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
-                                             ctypes.c_void_p(dtheta.data_ptr()), dtheta.stride(0), dtheta.stride(1),
-                                             _stream_ptr(dev))
+    args = (ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c), ctypes.c_void_p(_workspace(dev).data_ptr()),
+            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+            ctypes.c_void_p(dtheta.data_ptr()), dtheta.stride(0), dtheta.stride(1))
+    if exchange is not None:
+      st = lib.ikl_lagrangian_forward_backward_allreduce(*args, exchange.byref(), _stream_ptr(dev))
+    else:
+      st = lib.ikl_lagrangian_forward_backward(*args, _stream_ptr(dev))
   _cabi.check(st, "ikl_lagrangian_forward_backward")
   return out[:K], out[K], dtheta
 
@@ -207,8 +224,14 @@ def dual_update(lam, viol_sum, multiplier_lr, out=None):
   return out
 
 
+_CHECK_UNIT_UPSTREAM = os.environ.get("IKL_CHECK_UNIT_UPSTREAM", "0") == "1"      # tests: verify the promise (costs a device sync)
+
+
 class FusedIkLagrangian(torch.autograd.Function):
   """(constraint_violations[K], lagrange_loss[]) = f(theta, q_ee_desired, obstacles, lam).
+
+  unit_upstream=True is the caller's promise that backward() starts at lagrange_loss itself with gradient 1 (what
+  scripts/trainer.py:264 does); the scaling pass `dtheta * grad_loss` is then skipped.
 
   Differentiable w.r.t. theta only (targets, obstacles, limits and lam carry no gradient in the reference).
   When theta needs a gradient the forward launch already produces d(sum_i lam_i g_i)/d(theta); backward
@@ -217,9 +240,10 @@ class FusedIkLagrangian(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, theta, q_ee_desired, obstacles, lam, spec, lam_host=None):
+  def forward(ctx, theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False):
     ctx.set_materialize_grads(False)
     ctx.spec = spec
+    ctx.unit_upstream = bool(unit_upstream)
     weights = lam_host if lam_host is not None else lam
     if ctx.needs_input_grad[0]:
       viol, loss, dtheta = lagrangian_forward_backward(spec, theta.detach(), q_ee_desired, obstacles, weights)
@@ -234,16 +258,22 @@ class FusedIkLagrangian(torch.autograd.Function):
     theta, q_ee_desired, obstacles, lam, dtheta = ctx.saved_tensors
     if grad_viol is None:
       if grad_loss is None:
-        return None, None, None, None, None, None
-      return dtheta * grad_loss, None, None, None, None, None
+        return (None,) * 7
+      if ctx.unit_upstream:
+        # the caller differentiates lagrange_loss itself (scripts/trainer.py:264: outputs["lagrange_loss"].backward()), so
+        # the incoming gradient is 1 and the kernel's d(loss)/d(theta) is returned as written: no extra pass over (B,J)
+        if _CHECK_UNIT_UPSTREAM:
+          assert float(grad_loss) == 1.0, "unit_upstream=True but lagrange_loss received gradient %r" % float(grad_loss)
+        return dtheta, None, None, None, None, None, None
+      return dtheta * grad_loss, None, None, None, None, None, None
     lam_dev = lam if (isinstance(lam, torch.Tensor) and lam.is_cuda) else torch.as_tensor(lam, dtype=torch.float32, device=theta.device)
     w = grad_viol if grad_loss is None else grad_viol + grad_loss * lam_dev
     g = lagrangian_backward(ctx.spec, theta.detach(), q_ee_desired, obstacles, w.contiguous())
-    return g, None, None, None, None, None
+    return g, None, None, None, None, None, None
 
 
-def ik_lagrangian(theta, q_ee_desired, obstacles, lam, spec, lam_host=None):
+def ik_lagrangian(theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False):
   """Functional form of FusedIkLagrangian: returns (constraint_violations, lagrange_loss)."""
   if not isinstance(lam, torch.Tensor):
     lam = torch.as_tensor(lam, dtype=torch.float32)
-  return FusedIkLagrangian.apply(theta, q_ee_desired, obstacles, lam, spec, lam_host)
+  return FusedIkLagrangian.apply(theta, q_ee_desired, obstacles, lam, spec, lam_host, unit_upstream)

@@ -34,7 +34,7 @@ def _worker(rank, world, port, tmpdir):
   dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
   try:
     tr, fx = _build(tmpdir, "rank%d" % rank)
-    assert tr.world == world and tr.train_loader.batch_size == 64 // world
+    assert tr.world == world and tr.train_loader.batch_sampler.batch_size == 64
     for _ in range(3):
       tr.train_with_relaxation(tr.lambda_multipliers)
       tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
@@ -87,3 +87,83 @@ def test_one_process_driving_two_devices():
     results.append(out)
   for a, b in zip(*results):
     assert torch.equal(a, b)
+
+
+def _exchange_worker(rank, world, port, tmpdir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  for p in (ROOT, FUSED_OVERLAY, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  torch.cuda.set_device(rank)
+  dev = torch.device("cuda", rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+  try:
+    from ikl import ConstraintSpec, fused, synthetic, _cabi
+    from ikl.exchange import PeerExchange
+    ex = PeerExchange(device=dev)
+    for name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_1obs_static", "cfg_no_constraints"):
+      spec = ConstraintSpec.from_config(config_json(name), 3, 0.005, 1.0)
+      K = spec.num_constraints
+      lam = [0.5 + 0.1 * i for i in range(K)]
+      for B in (4096 + 512 * rank, 8):                      # ragged across ranks; tiny (strided kernel) too
+        theta, q_des, obst = synthetic.make_batch(B, seed=17 + rank, device=str(dev))
+        for layout in ("rows", "planes"):
+          args = synthetic.to_planes(theta, q_des, obst, max(spec.num_obstacles, 1)) if layout == "planes" else (theta, q_des, obst)
+          ob = args[2] if spec.dynamic else None
+          local, lloss, g_local = fused.lagrangian_forward_backward(spec, args[0], args[1], ob, lam)
+          accum = torch.zeros(K, dtype=torch.float64, device=dev)
+          for rep in range(3):                                # consecutive launches alternate the mailbox parity
+            glob, gloss, g = fused.lagrangian_forward_backward(spec, args[0], args[1], ob, lam, viol_accum=accum, exchange=ex)
+          assert torch.equal(g, g_local), "d/dtheta of the shard does not depend on the exchange"
+          parts = [torch.zeros(K, dtype=torch.float64, device=dev) for _ in range(world)]
+          dist.all_gather(parts, local.double())
+          want = torch.stack(parts).sum(0)
+          scale = torch.stack(parts).abs().sum(0).clamp(min=1e-30)
+          assert float(((glob.double() - want).abs() / scale).max()) <= 1e-6, (name, B, layout)
+          assert float(((accum / 3 - want).abs() / scale).max()) <= 1e-6
+          both = [torch.zeros_like(glob) for _ in range(world)]
+          dist.all_gather(both, glob)
+          assert torch.equal(both[0], both[1]), "global sums must be bit-identical on every rank"
+          want_loss = float((torch.tensor(lam, dtype=torch.float64, device=dev) * want).sum())
+          assert abs(float(gloss) - want_loss) <= 1e-5 * float((torch.tensor(lam, dtype=torch.float64, device=dev) * scale).sum())
+          fwd = fused.lagrangian_forward(spec, args[0], args[1], ob, lam, exchange=ex)
+          assert torch.equal(fwd["constraint_violations"], glob), "forward-only and fwd+bwd launches exchange the same sums"
+    # CUDA-graph replay: the sequence counter lives on the device, so replays pair up across ranks
+    spec = ConstraintSpec.from_config(config_json(NAME), 3, 0.005, 1.0)
+    lam = [1.0] * 16
+    theta, q_des, obst = synthetic.make_batch(8192, seed=40 + rank, device=str(dev))
+    out = torch.empty(17, device=dev)
+    dth = torch.empty_like(theta)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam, dtheta=dth, out=out, exchange=ex)
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=side):
+        for _ in range(5):
+          fused.lagrangian_forward_backward(spec, theta, q_des, obst, lam, dtheta=dth, out=out, exchange=ex)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    first = out.clone()
+    for _ in range(4):
+      graph.replay()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(out, first)
+    both = [torch.zeros_like(out) for _ in range(world)]
+    dist.all_gather(both, out)
+    assert torch.equal(both[0], both[1])
+    open(os.path.join(tmpdir, "ex_ok_%d" % rank), "w").write("ok")
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_in_kernel_peer_exchange_of_the_sums(tmp_path):
+  """The fused kernel all-reduces the K sums itself over NVLink peer memory (include/ikl.h IklExchange): global sums are
+  bit-identical on both ranks, equal the float64 sum of the local sums, and the shard gradient is untouched."""
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert (tmp_path / "ex_ok_0").exists() and (tmp_path / "ex_ok_1").exists()

@@ -295,6 +295,24 @@ def test_penalty_dropins_accept_trainer_style_views(cuda_device):
   np.testing.assert_allclose(got2.detach().cpu().numpy(), ref2.numpy(), rtol=0, atol=3e-7)
 
 
+def test_dropins_refuse_dtypes_they_would_have_to_narrow(cuda_device):
+  """The reference's functions are dtype-generic (a float64 tensor is evaluated in float64); the CUDA drop-ins compute in
+  float32 only and say so instead of narrowing silently."""
+  import kinematics.forward_kinematics as fk
+  import kinematics.penalties as pen
+  th = torch.zeros(4, 3, dtype=torch.float64, device=cuda_device)
+  with pytest.raises(TypeError):
+    fk.ForwardKinematicsThreeLinkTorch(th)
+  z = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+  with pytest.raises(TypeError):
+    pen.piecewise_circle_penalty(z, z, z, z, z)
+  with pytest.raises(TypeError):
+    pen.piecewise_joint_limit_penalty(z.float(), z, z)
+  # python scalars and float32 tensors mix, as in test/test_training_utils.py of the reference
+  out = pen.piecewise_circle_penalty(torch.zeros(3, device=cuda_device), torch.zeros(3, device=cuda_device), 1.0, 0.0, 0.25)
+  assert out.dtype == torch.float32 and out.shape == (3,)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # level (ii): the fused Lagrangian
 # ------------------------------------------------------------------------------------------------------------

@@ -364,3 +364,108 @@ def test_trainer_with_device_resident_data(tmp_path, cuda_device):
   assert not torch.equal(tr.lambda_multipliers, lam0) and bool((tr.lambda_multipliers >= 0).all())
   assert any(not torch.equal(a, b) for a, b in zip(w0, tr.model.parameters()))
   assert all(torch.isfinite(p).all() for p in tr.model.parameters())
+
+
+def test_graph_capture_keeps_a_loaded_optimizer_state(cuda_device):
+  """--cuda_graph --load_adam: capturing the step warms up on dummy data, which must not disturb the Adam moments and the
+  step count that were there before (a resumed run), nor the weights; a fresh optimizer must come out at step 0."""
+  from ikl import ConstraintSpec, synthetic
+  from ikl.graph_step import GraphedTrainStep
+  from ikl import fused
+  from models.simple_network import SimpleNetwork
+  spec = ConstraintSpec.from_config(config_json("cfg_joint_limits_and_4obs_dynamic"), 3, 0.005, 1.0)
+  B = 64
+  _, q_des, obst = synthetic.make_batch(B, seed=5, device="cuda:0")
+  x = torch.randn(B, 20, device=cuda_device)
+  inputs = {"input_tensor": x, "q_ee_desired": q_des, "dynamic_obstacles": obst}
+  lam = torch.linspace(0.5, 2.0, 16, device=cuda_device)
+  torch.manual_seed(3)
+  model = SimpleNetwork(20, 3, hidden_units=16, depth=8, dropout=0.0).to(cuda_device)
+  opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+
+  def eager_step(m, o):
+    viol, loss = fused.FusedIkLagrangian.apply(m(x), q_des, obst, lam, spec)
+    o.zero_grad()
+    loss.backward()
+    o.step()
+  for _ in range(3):                                     # "the run before the checkpoint": builds non-trivial Adam state
+    eager_step(model, opt)
+  import copy
+  twin = copy.deepcopy(model)
+  twin_opt = torch.optim.Adam(twin.parameters(), lr=1e-3, capturable=True)
+  twin_opt.load_state_dict(copy.deepcopy(opt.state_dict()))
+  before = {k: v.clone() for k, v in model.state_dict().items()}
+  before_opt = [{k: v.clone() for k, v in opt.state[p].items()} for p in model.parameters()]
+  g = GraphedTrainStep(model, opt, spec, B, cuda_device)
+  for k, v in model.state_dict().items():
+    assert torch.equal(v, before[k]), k
+  for p, st in zip(model.parameters(), before_opt):
+    for k, v in st.items():
+      assert torch.equal(opt.state[p][k], v), k
+    assert float(opt.state[p]["step"]) == 3.0
+  g.set_multipliers(lam)
+  for _ in range(2):
+    g.step(inputs)
+    eager_step(twin, twin_opt)
+  for a, b in zip(model.parameters(), twin.parameters()):
+    assert float((a - b).detach().abs().max()) <= 2e-6 * max(1.0, float(b.detach().abs().max()))
+  # a fresh optimizer: capture leaves it at step 0 with zero moments
+  m2 = SimpleNetwork(20, 3, hidden_units=16, depth=8, dropout=0.0).to(cuda_device)
+  o2 = torch.optim.Adam(m2.parameters(), lr=1e-3, capturable=True)
+  GraphedTrainStep(m2, o2, spec, B, cuda_device)
+  for p in m2.parameters():
+    assert float(o2.state[p]["step"]) == 0.0 and float(o2.state[p]["exp_avg"].abs().max()) == 0.0
+
+
+def test_device_data_with_cuda_graph_on_a_dynamic_config(tmp_path, cuda_device):
+  """--device_data --cuda_graph: the loaders hand (B,4,3) obstacle PLANES; the graph's static buffers are planes too and the
+  TMA-staged planes kernel is the one captured.  Same weights as the eager --device_data run from the same state."""
+  from ikl.configs import write_config
+  from ikl import _cabi
+  from models.simple_network import SimpleNetwork
+  from scripts.options import Options
+  from scripts.trainer import IkLagrangeDualTrainer
+  cfg_path = write_config(config_json("cfg_joint_limits_and_4obs_dynamic"), str(tmp_path / "cfg.json"))
+  trainers = []
+  for tag, extra in (("eager", []), ("graph", ["--cuda_graph"])):
+    opt = Options().parse(["--model_name", tag, "--config_file", cfg_path, "--log_dir", str(tmp_path), "--device_data",
+                           "--train_dataset_size", "16384", "--val_dataset_size", "4096", "--batch_size", "4096", "--lagrange_iters", "2",
+                           "--train_iters", "4", "--hidden_units", "32", "--initial_lambda", "1", "--penalty_good_slope", "0.005",
+                           "--model_save_hz", "1000"] + extra)
+    tr = IkLagrangeDualTrainer(opt)
+    torch.manual_seed(11)
+    tr.model = SimpleNetwork(20, 3, hidden_units=32, depth=8, dropout=0.0).to(tr.device)
+    tr.optimizer = torch.optim.Adam(tr.model.parameters(), lr=opt.optimizer_lr, betas=(0.9, 0.999), capturable=tr.use_graph)
+    trainers.append(tr)
+  eager, graph = trainers
+  graph.model.load_state_dict(eager.model.state_dict())
+  assert graph.use_graph and not eager.use_graph
+  for tr in trainers:
+    for _ in range(2):
+      tr.train_with_relaxation(tr.lambda_multipliers)
+      tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
+  assert graph._graph_step is not None and graph._graph_step.planes
+  assert graph._graph_step.obst.stride(0) == 1 and graph._graph_step.q_des.stride(0) == 1
+  assert float((eager.lambda_multipliers - graph.lambda_multipliers).abs().max()) <= 1e-5 * float(eager.lambda_multipliers.abs().max())
+  for a, b in zip(eager.model.parameters(), graph.model.parameters()):
+    assert float((a - b).detach().abs().max()) <= 2e-5 * max(1.0, float(a.detach().abs().max()))
+
+
+def test_unit_upstream_skips_the_scaling_pass_and_is_checked(cuda_device, monkeypatch):
+  from ikl import ConstraintSpec, synthetic, fused
+  spec = ConstraintSpec.from_config(config_json("cfg_joint_limits_and_4obs_dynamic"), 3, 0.005, 1.0)
+  theta, q_des, obst = synthetic.make_batch(1024, seed=9, device="cuda:0")
+  lam = torch.linspace(0.5, 2.0, 16, device=cuda_device)
+  grads = []
+  for unit in (False, True):
+    th = theta.clone().requires_grad_(True)
+    viol, loss = fused.FusedIkLagrangian.apply(th, q_des, obst, lam, spec, None, unit)
+    loss.backward()
+    grads.append(th.grad.clone())
+  assert torch.equal(grads[0], grads[1])
+  # the promise is checkable: a scaled loss with unit_upstream=True trips the (opt-in) assertion
+  monkeypatch.setattr(fused, "_CHECK_UNIT_UPSTREAM", True)
+  th = theta.clone().requires_grad_(True)
+  viol, loss = fused.FusedIkLagrangian.apply(th, q_des, obst, lam, spec, None, True)
+  with pytest.raises(AssertionError):
+    (2.0 * loss).backward()

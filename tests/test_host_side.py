@@ -145,13 +145,23 @@ def _worker(rank, world, port, tmpdir):
     assert torch.equal(both[0], both[1]), "lambda must be bit-identical on every rank"
     torch.testing.assert_close(lam_new, O.dual_update(lam, ref["constraint_violations"].detach().unsqueeze(0), 1e-3), rtol=1e-5, atol=1e-6)
     # loaders: the ranks' shares of an epoch partition the dataset
-    ds = torch.utils.data.TensorDataset(torch.arange(40))
-    loader = D.make_loader(ds, 8, 0)
-    seen = torch.cat([b[0] for b in loader])
-    assert loader.batch_size == 4 and len(seen) == 20
-    allseen = [torch.zeros_like(seen) for _ in range(world)]
-    dist.all_gather(allseen, seen)
-    assert sorted(torch.cat(allseen).tolist()) == list(range(40))
+    class Items(torch.utils.data.Dataset):          # dict items, like IkDataset.__getitem__ (kinematics/dataset.py:143-155)
+      def __len__(self):
+        return 41                                    # NOT divisible by the world size or the batch size
+
+      def __getitem__(self, i):
+        return {"idx": torch.tensor(i), "row": torch.full((3,), float(i))}
+    loader = D.make_loader(Items(), 8, 0)
+    batches = list(loader)
+    assert len(batches) == 6 and batches[0]["idx"].shape == (4,) and batches[0]["row"].shape == (4, 3)
+    assert batches[-1]["idx"].shape == ((1,) if rank == 0 else (0,)) and batches[-1]["row"].shape[1:] == (3,)    # ragged tail: 1 + 0
+    seen = torch.cat([b["idx"] for b in batches])
+    padded = torch.full((21,), -1, dtype=seen.dtype)
+    padded[:len(seen)] = seen
+    allseen = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(allseen, padded)
+    got = torch.cat(allseen)
+    assert sorted(got[got >= 0].tolist()) == list(range(41)), "every sample exactly once: nothing padded, nothing dropped"
     with open(os.path.join(tmpdir, "ok_%d" % rank), "w") as f:
       f.write("ok")
   finally:
@@ -209,3 +219,66 @@ def test_device_batch_loader_covers_the_dataset_and_shards_by_rank():
     assert len(set(ids.long().tolist())) == len(ids)
   all_ids = torch.cat([b["joint_theta"][:, 0] for p in parts for b in p]) / 3
   assert sorted(all_ids.long().tolist()) == list(range(n))
+
+
+# ---- sharding without padding, lazy outputs ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,bs,world", [(4001, 8, 3), (32, 8, 2), (10, 4, 4), (7, 16, 2), (4000, 8, 8)])
+def test_sharded_batch_sampler_counts_every_sample_exactly_once(n, bs, world):
+  """The dual step adds the constraint sums over the WHOLE validation set (trainer.py:274-280): under any world size every
+  sample must be seen exactly once (DistributedSampler(drop_last=False) repeats samples when n % world != 0), and every
+  rank must see the same number of batches so that the collectives of a step pair up."""
+  from ikl.dist import ShardedBatchSampler
+  per_rank = [list(ShardedBatchSampler(n, bs, r, world, shuffle=True, seed=3)) for r in range(world)]
+  assert len({len(b) for b in per_rank}) == 1 and len(per_rank[0]) == (n + bs - 1) // bs
+  seen = sorted(i for batches in per_rank for b in batches for i in b)
+  assert seen == list(range(n))
+  for g in range(len(per_rank[0])):                                  # a global batch is dealt round-robin
+    sizes = [len(per_rank[r][g]) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1 and sum(sizes) == min(bs, n - g * bs)
+  s0 = ShardedBatchSampler(n, bs, 0, world, shuffle=True, seed=3)
+  first = list(s0)
+  s0.set_epoch(1)
+  assert list(s0) != first or n <= 1
+
+
+def test_loader_collates_an_empty_share():
+  from ikl.dist import _CollateWithEmpty
+  ds = [{"a": torch.zeros(3), "b": torch.zeros(4, 4)} for _ in range(5)]
+  c = _CollateWithEmpty(ds)
+  out = c([])
+  assert out["a"].shape == (0, 3) and out["b"].shape == (0, 4, 4)
+  assert c(ds[:2])["b"].shape == (2, 4, 4)
+
+
+def test_batch_outputs_behaves_like_the_reference_dict():
+  """process_batch's outputs are a plain dict in the reference (trainer.py:163): get / items / values / iteration / len /
+  dict() must all expose the lazily materialised entries."""
+  from scripts.trainer import BatchOutputs
+  calls = []
+
+  def side(out):
+    calls.append("side")
+    dict.__setitem__(out, "q_ee_actual", 1)
+    dict.__setitem__(out, "position_err_sq", 2)
+    out._lazy.pop("q_ee_actual", None)
+    out._lazy.pop("position_err_sq", None)
+
+  def l2(out):
+    calls.append("l2")
+    dict.__setitem__(out, "joint_angle_l2", 3)
+
+  def fresh():
+    o = BatchOutputs({"q_ee_actual": side, "position_err_sq": side, "joint_angle_l2": l2})
+    o["lagrange_loss"] = 0
+    return o
+  o = fresh()
+  assert len(o) == 4 and "q_ee_actual" in o and set(o.keys()) == {"lagrange_loss", "q_ee_actual", "position_err_sq", "joint_angle_l2"}
+  assert calls == []                                      # nothing materialised yet
+  assert o.get("q_ee_actual") == 1 and o.get("position_err_sq") == 2 and calls == ["side"]      # one launch fills both
+  assert o.get("nope", 7) == 7
+  assert dict(fresh()) == {"lagrange_loss": 0, "q_ee_actual": 1, "position_err_sq": 2, "joint_angle_l2": 3}
+  assert sorted(fresh().values()) == [0, 1, 2, 3]
+  assert sorted(k for k, _ in fresh().items()) == sorted(fresh().keys()) == sorted(iter(fresh()))
+  assert fresh()["joint_angle_l2"] == 3
+  with pytest.raises(KeyError):
+    fresh()["missing"]
