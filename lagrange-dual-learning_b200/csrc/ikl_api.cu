@@ -116,12 +116,37 @@ void fill_packed_uniforms(const IklSpec* spec, const Uniforms& u, PackedUniforms
   pu.jl_sdiff = dup(smax - smin);
   pu.ob_nlo = dup(-u.ob_lo);
   pu.ob_ndiff = dup(u.ob_lo - u.ob_hi);
+  pu.ob_nhi_sel = dup(fmaf(1.0f, u.ob_lo - u.ob_hi, -u.ob_lo));
+  pu.jl_shi_sel = dup(fmaf(1.0f, smax - smin, smin));
   for (int o = 0; o < kMaxObst; ++o)
     for (int c = 0; c < 3; ++c) pu.stat_ob[o][c] = dup(u.stat_ob[o][c]);
   for (int o = 0; o < kMaxObst; ++o) pu.stat_thr[o] = dup(u.stat_ob[o][2] * kNearTie);      // fl(r * 2^-20): exact scaling
   for (int i = 0; i < kMaxK; ++i) pu.lam[i] = dup(u.w[i]);
+  for (int m = 0; m < kMaxLinks; ++m) pu.link[m] = dup(u.link[m]);
 }
 
+
+// Static obstacles as pairs (2q, 2q+1) for the single-sample kernels (eval_single_static); an odd count repeats the last
+// obstacle in the padding lane with weight 0.
+void fill_static_pairs(const IklSpec* spec, const Uniforms& u, StaticPairUniforms& sp) {
+  memset(&sp, 0, sizeof(sp));
+  const int n = spec->num_obstacles, J = 3;
+  const int base = 1 + (spec->enforce_joint_limits ? J : 0);
+  for (int q = 0; q < kMaxObstPairs; ++q) {
+    const int o0 = 2 * q < n ? 2 * q : (n > 0 ? n - 1 : 0);
+    const int o1 = 2 * q + 1 < n ? 2 * q + 1 : o0;
+    sp.ox[q] = make_float2(u.stat_ob[o0][0], u.stat_ob[o1][0]);
+    sp.oy[q] = make_float2(u.stat_ob[o0][1], u.stat_ob[o1][1]);
+    sp.nr[q] = make_float2(-u.stat_ob[o0][2], -u.stat_ob[o1][2]);
+    sp.thr[q] = make_float2(u.stat_ob[o0][2] * kNearTie, u.stat_ob[o1][2] * kNearTie);
+    for (int m = 0; m < J; ++m) {
+      const int j = J - 1 - m;                       // tip m is FK tuple index j (end effector first)
+      const float w0 = 2 * q < n ? u.w[base + 3 * (2 * q) + j] : 0.f;
+      const float w1 = 2 * q + 1 < n ? u.w[base + 3 * (2 * q + 1) + j] : 0.f;
+      sp.lam[m][q] = make_float2(w0, w1);
+    }
+  }
+}
 
 // ---- TMA descriptors ---------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled lives in the driver; libikl.so links cudart statically and asks it for the entry point.
@@ -171,7 +196,7 @@ bool unit_links(const IklSpec* spec) {
 int detect_layout(const IklSpec* spec, const IklBatch* in, bool grad, const float* dtheta, int64_t dt_sb, int64_t dt_sj) {
   const int J = spec->num_links;
   const bool dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles;
-  if (J != 3 || !unit_links(spec) || in->batch < 2) return kStrided;
+  if ((J != 2 && J != 3) || in->batch < 2) return kStrided;
   const bool rows = in->theta_sj == 1 && in->theta_sb == J && in->target_sc == 1 && in->target_sb >= 2 &&
                     (!dyn || (in->obst_sc == 1 && in->obst_so == 4 && in->obst_sb == 4 * kMaxObst && aligned16(in->obstacles))) &&
                     (!grad || (dt_sj == 1 && dt_sb == J));
@@ -192,6 +217,7 @@ int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const flo
   memset(&p, 0, sizeof(p));
   fill_uniforms(spec, w_host, p.u);
   fill_packed_uniforms(spec, p.u, p.pu);
+  if (spec->num_links == 3 && !(spec->num_obstacles > 0 && spec->dynamic_obstacles)) fill_static_pairs(spec, p.u, p.sp);
   p.batch = in->batch;
   p.theta = in->theta;    p.th_sb = in->theta_sb;  p.th_sj = in->theta_sj;
   p.target = in->target;  p.tg_sb = in->target_sb; p.tg_sc = in->target_sc;
@@ -202,6 +228,8 @@ int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const flo
   v.dyn = spec->num_obstacles > 0 && spec->dynamic_obstacles != 0;
   v.jl = spec->enforce_joint_limits != 0;
   v.mode = kFwd;
+  v.links = spec->num_links;
+  v.unit = unit_links(spec);
 
   int layout = detect_layout(spec, in, grad, dtheta, dt_sb, dt_sj);
   if (layout == kPlanes) {
@@ -213,7 +241,7 @@ int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const flo
                 in->theta_sj % 4 == 0 && aligned16(in->target) && in->target_sc % 4 == 0 &&
                 (!dyn || (aligned16(in->obstacles) && in->obst_so % 4 == 0 && in->obst_sc % 4 == 0));
     if (p.use_tma) {
-      p.use_tma = encode_planes(&p.tm_theta, in->theta, in->batch, 3, in->theta_sj, 0, 0) &&
+      p.use_tma = encode_planes(&p.tm_theta, in->theta, in->batch, spec->num_links, in->theta_sj, 0, 0) &&
                   encode_planes(&p.tm_target, in->target, in->batch, 2, in->target_sc, 0, 0) &&
                   (!dyn || encode_planes(&p.tm_obst, in->obstacles, in->batch, 3, in->obst_sc, v.nobs, in->obst_so));
     }
@@ -268,8 +296,16 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   cudaStream_t cs = (cudaStream_t)stream;
   bool found = false;
   cudaError_t e = cudaSuccess;
-  if (layout == kRows) e = launch_family<kRows, 3, true>(v, p, cs, kMaxGrid, &found);
-  else if (layout == kPlanes) e = launch_family<kPlanes, 3, true>(v, p, cs, kMaxGrid, &found);
+  // packed families: 3 links with the unit lengths folded (the reference's arm), 3 links with runtime lengths, 2 links
+  if (layout == kRows) {
+    if (v.links == 3 && v.unit) e = launch_family<kRows, 3, true>(v, p, cs, kMaxGrid, &found);
+    else if (v.links == 3) e = launch_family<kRows, 3, false>(v, p, cs, kMaxGrid, &found);
+    else e = launch_family<kRows, 2, false>(v, p, cs, kMaxGrid, &found);
+  } else if (layout == kPlanes) {
+    if (v.links == 3 && v.unit) e = launch_family<kPlanes, 3, true>(v, p, cs, kMaxGrid, &found);
+    else if (v.links == 3) e = launch_family<kPlanes, 3, false>(v, p, cs, kMaxGrid, &found);
+    else e = launch_family<kPlanes, 2, false>(v, p, cs, kMaxGrid, &found);
+  }
   if (!found) {
     if (forced == kRows || forced == kPlanes) return IKL_ERR_UNSUPPORTED;
     if (spec->num_links == 3) e = launch_family<kStrided, 3, false>(v, p, cs, kMaxGrid, &found);

@@ -240,7 +240,7 @@ IklStatus ikl_eval_stats(const IklSpec* spec, const IklBatch* in, float threshol
     Variant v;
     const int layout = prepare_lagrangian_params(spec, in, nullptr, false, nullptr, 0, 0, lp, v);
     if (layout < 0) return (IklStatus)(-layout);
-    if ((layout == kRows || layout == kPlanes) && lp.use_tma) {
+    if ((layout == kRows || layout == kPlanes) && lp.use_tma && v.links == 3 && v.unit) {
       lp.stats_threshold = threshold;
       lp.stats_counts = reinterpret_cast<unsigned long long*>(counts_out);
       lp.stats_pos_err = pos_err_sum_out;

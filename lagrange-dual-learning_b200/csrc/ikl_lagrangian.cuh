@@ -65,6 +65,7 @@ struct ExchangeBuf {
 struct LagrangianParams {
   Uniforms u;
   PackedUniforms pu;
+  StaticPairUniforms sp;
   long long batch;
   const float* theta;   long long th_sb, th_sj;
   const float* target;  long long tg_sb, tg_sc;
@@ -282,9 +283,9 @@ struct WarpSharedAcc {
   }
   // Rows pipeline: the thread keeps the sums of obstacle (k ^ r) in obstacle slot k (see run_rows_pipe); put them back
   // in constraint order before the lanes (which have different r) are added together.
-  template <int OBASE>
+  template <int OBASE, int J>
   __device__ __forceinline__ void flush_xor4(f2 (&acc)[K], int r) {
-    static_assert(K == OBASE + 12 && N == 16, "four obstacles x three tips");
+    static_assert(K == OBASE + 4 * J, "four obstacles x J tips");
     float v[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = i < K ? f2_lo(acc[i]) + f2_hi(acc[i]) : 0.f;
@@ -297,10 +298,10 @@ struct WarpSharedAcc {
       for (int k = 0; k < 4; ++k) {
         if (k & bit) continue;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float a = v[OBASE + 3 * k + j], b = v[OBASE + 3 * (k | bit) + j];
-          v[OBASE + 3 * k + j] = sw ? b : a;
-          v[OBASE + 3 * (k | bit) + j] = sw ? a : b;
+        for (int j = 0; j < J; ++j) {
+          const float a = v[OBASE + J * k + j], b = v[OBASE + J * (k | bit) + j];
+          v[OBASE + J * k + j] = sw ? b : a;
+          v[OBASE + J * (k | bit) + j] = sw ? a : b;
         }
       }
     }
@@ -483,9 +484,9 @@ __device__ __forceinline__ void run_planes_packed(const LagrangianParams& p, con
   int since_flush = 0;
   for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < npair; v += step) {
     const long long b = v << 1;
-    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
+    f2 th[C::J], ob[C::NOB][3], dth[C::J], ee[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) th[j] = ldg_stream_f2(p.theta + j * p.th_sj + b);
+    for (int j = 0; j < C::J; ++j) th[j] = ldg_stream_f2(p.theta + j * p.th_sj + b);
     const f2 tx = ldg_stream_f2(p.target + b);
     const f2 ty = ldg_stream_f2(p.target + p.tg_sc + b);
     if (C::DYN) {
@@ -497,10 +498,10 @@ __device__ __forceinline__ void run_planes_packed(const LagrangianParams& p, con
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
+      for (int j = 0; j < C::J; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
     } else {
       store_side_outputs(p, b, b + 1, ee, tx, ty);
     }
@@ -525,11 +526,11 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
   int since_flush = 0;
   for (long long base = (long long)blockIdx.x * kTile; base < full; base += (long long)gridDim.x * kTile) {
     const long long bA = base + threadIdx.x, bB = bA + kThreads;
-    f2 th[3], ob[C::NOB][3], dth[3], ee[3];
-    const float* tA = p.theta + bA * 3;
-    const float* tB = p.theta + bB * 3;
+    f2 th[C::J], ob[C::NOB][3], dth[C::J], ee[3];
+    const float* tA = p.theta + bA * C::J;
+    const float* tB = p.theta + bB * C::J;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) th[j] = f2_make(ldg_stream1(tA + j), ldg_stream1(tB + j));
+    for (int j = 0; j < C::J; ++j) th[j] = f2_make(ldg_stream1(tA + j), ldg_stream1(tB + j));
     const float* gA = p.target + bA * p.tg_sb;
     const float* gB = p.target + bB * p.tg_sb;
     const f2 tx = f2_make(ldg_stream1(gA), ldg_stream1(gB));
@@ -547,12 +548,12 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
-      float* dA = p.dtheta + bA * 3;
-      float* dB = p.dtheta + bB * 3;
+      float* dA = p.dtheta + bA * C::J;
+      float* dB = p.dtheta + bB * C::J;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < C::J; ++j) {
         dA[j] = f2_lo(dth[j]);
         dB[j] = f2_hi(dth[j]);
       }
@@ -570,10 +571,10 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
 #pragma unroll
   for (int i = 0; i < C::K; ++i) sacc1[i] = 0.f;
   for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < B; b += (long long)gridDim.x * kThreads) {
-    float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3];
+    float th[C::J], tx, ty, ob[C::NOB][3], dth[C::J], ee[3];
     if (!C::DYN) static_obstacles<C>(p, ob);
     load_sample<C>(p, b, th, tx, ty, ob);
-    eval_sample<3, C::NOBS, C::JL, C::GRAD, true>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
+    eval_sample<C::J, C::NOBS, C::JL, C::GRAD, C::UNIT>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
     store_sample<C>(p, b, dth, ee, tx, ty);
   }
   sacc.flush(sacc1);
@@ -714,6 +715,8 @@ struct Variant {
   int nobs;
   bool dyn, jl;
   int mode;
+  int links;      // J
+  bool unit;      // every link length is exactly 1 (the compile-time-folded families)
 };
 
 // Instantiated once per family in ikl_lagrangian_<family>.cu.

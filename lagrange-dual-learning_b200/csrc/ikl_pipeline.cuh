@@ -72,7 +72,7 @@ constexpr int kTmaBoxBytes = kTmaBox * 4;
 #endif
 template <class C>
 struct TmaLayout {
-  static constexpr int kPlanes = 5 + (C::DYN ? 3 * C::NOBS : 0);
+  static constexpr int kPlanes = C::J + 2 + (C::DYN ? 3 * C::NOBS : 0);
   static constexpr int kHalfBytes = kPlanes * kTmaBoxBytes;
   static constexpr int kStageBytes = (kTmaTile / kTmaBox) * kHalfBytes;
   static constexpr int kStages = IKL_TMA_STAGES;
@@ -84,9 +84,9 @@ struct TmaLayout {
 // stored again.  Not inlined: it costs the hot loop no registers, and it runs for about one pair in a million.
 template <class C, class W2>
 static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, const W2& w2, long long bA, long long bB) {
-  f2 th[3], ob[C::NOB][3], acc[C::K], dth[3], ee[3];
+  f2 th[C::J], ob[C::NOB][3], acc[C::K], dth[C::J], ee[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) th[j] = f2_make(p.theta[bA * p.th_sb + j * p.th_sj], p.theta[bB * p.th_sb + j * p.th_sj]);
+  for (int j = 0; j < C::J; ++j) th[j] = f2_make(p.theta[bA * p.th_sb + j * p.th_sj], p.theta[bB * p.th_sb + j * p.th_sj]);
   const f2 tx = f2_make(p.target[bA * p.tg_sb], p.target[bB * p.tg_sb]);
   const f2 ty = f2_make(p.target[bA * p.tg_sb + p.tg_sc], p.target[bB * p.tg_sb + p.tg_sc]);
   if (C::DYN) {
@@ -101,9 +101,9 @@ static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, c
   }
 #pragma unroll
   for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  eval_pair<C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+  eval_pair<C::J, C::UNIT, C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < C::J; ++j) {
     p.dtheta[bA * p.dt_sb + j * p.dt_sj] = f2_lo(dth[j]);
     p.dtheta[bB * p.dt_sb + j * p.dt_sj] = f2_hi(dth[j]);
   }
@@ -126,8 +126,8 @@ struct LagrangianBody {
   const f2 ndiff;                 // lo - hi slope of the circle penalty, in registers (see eval_pair)
   f2 acc[C::K];
   int since_flush;
-  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
+  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN && C::NOBS == kMaxObst;
+  static constexpr int kObstBase = 1 + (C::JL ? C::J : 0);
   // cheap distances (see ikl_packed.cuh) in the forward-only and the gradient kernels alike, so both report the same
   // sums bit for bit; the gradient kernels redo near-tie pairs exactly
   static constexpr bool kExact = C::NOBS == 0 || IKL_EXACT_GRAD;
@@ -137,18 +137,18 @@ struct LagrangianBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
   }
-  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
-    f2 dth[3], ee[3];
-    const bool near_tie = eval_pair<C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, ndiff);
+  __device__ __forceinline__ void pair(const f2 (&th)[C::J], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
+    f2 dth[C::J], ee[3];
+    const bool near_tie = eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, ndiff);
     if (C::GRAD) {
       if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
 #pragma unroll
-        for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + bA, dth[j]);
+        for (int j = 0; j < C::J; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + bA, dth[j]);
       } else {
-        float* dA = p.dtheta + bA * 3;
-        float* dB = p.dtheta + bB * 3;
+        float* dA = p.dtheta + bA * C::J;
+        float* dB = p.dtheta + bB * C::J;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < C::J; ++j) {
           dA[j] = f2_lo(dth[j]);
           dB[j] = f2_hi(dth[j]);
         }
@@ -161,8 +161,137 @@ struct LagrangianBody {
     }
   }
   __device__ __forceinline__ void flush() {
-    if constexpr (kPermuted) sacc.template flush_xor4<kObstBase>(acc, r);
+    if constexpr (kPermuted) sacc.template flush_xor4<kObstBase, C::J>(acc, r);
     else sacc.flush(acc);
+  }
+  __device__ __forceinline__ void tile_done() {
+    if (++since_flush == kFlushSamples / 2) {
+      since_flush = 0;
+      flush();
+    }
+  }
+  __device__ __forceinline__ void finish() { flush(); }
+};
+
+// SingleStaticBody: the Lagrangian body for configs with a STATIC obstacle table.  The pipelines still hand over a pair of
+// samples; the body evaluates them one after the other (a two-trip loop that is deliberately not unrolled) with
+// eval_single_static, whose packed lanes are obstacle pairs.  Half the live state of LagrangianBody -- 16 running sums
+// instead of 32 -- so these FP32-latency-bound kernels fit a third / fourth resident block per SM (staged_min_blocks).
+#ifndef IKL_STATIC_SINGLE
+#define IKL_STATIC_SINGLE 0
+#endif
+struct SingleHostWeights {
+  const LagrangianParams& p;
+  __device__ __forceinline__ float lam_s(int i) const { return p.u.w[i]; }
+  __device__ __forceinline__ f2 lam_ob(int m, int q) const { return as_f2(p.sp.lam[m][q]); }
+};
+struct SingleSmemWeights {
+  const float* lam;                 // K multipliers
+  const float2* lam_pairs;          // [3][kMaxObstPairs]
+  __device__ __forceinline__ float lam_s(int i) const { return lam[i]; }
+  __device__ __forceinline__ f2 lam_ob(int m, int q) const { return *reinterpret_cast<const f2*>(lam_pairs + m * kMaxObstPairs + q); }
+};
+
+// device-resident multipliers as obstacle pairs [tip m][pair q] (0 in a padding lane); threads 0 .. 3*kMaxObstPairs-1
+template <class C>
+__device__ __forceinline__ void stage_pair_weights(const float* w_dev, float2* lam_pairs) {
+  constexpr int base = 1 + (C::JL ? 3 : 0);
+  const int t = threadIdx.x;
+  if (t < 3 * kMaxObstPairs) {
+    const int m = t / kMaxObstPairs, q = t % kMaxObstPairs, j = 2 - m;
+    const float w0 = 2 * q < C::NOBS ? __ldg(w_dev + base + 3 * (2 * q) + j) : 0.f;
+    const float w1 = 2 * q + 1 < C::NOBS ? __ldg(w_dev + base + 3 * (2 * q + 1) + j) : 0.f;
+    lam_pairs[t] = make_float2(w0, w1);
+  }
+}
+
+template <class C>
+constexpr bool use_single_static() { return IKL_STATIC_SINGLE && !IKL_EXACT_GRAD && !C::DYN && C::NOBS > 0 && C::J == 3 && C::UNIT; }
+
+template <class C, class W1, class W2>
+struct SingleStaticBody {
+  const LagrangianParams& p;
+  const W1& w1;
+  const W2& w2_plain;               // packed multipliers in constraint order, for the exact redo of a near-tie pair
+  WarpSharedAcc<C::K>& sacc;
+  const f2 ndiff;
+  float acc_s[4];
+  f2 acc_ob[3][kMaxObstPairs];
+  int since_flush;
+  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
+  static constexpr int NP = (C::NOBS + 1) / 2;
+  __device__ __forceinline__ SingleStaticBody(const LagrangianParams& pp, const W1& w, const W2& w_plain, WarpSharedAcc<C::K>& sa,
+                                              const volatile float2* s_ndiff)
+      : p(pp), w1(w), w2_plain(w_plain), sacc(sa), ndiff(f2_make(s_ndiff->x, s_ndiff->y)), since_flush(0) {
+    clear();
+  }
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_s[i] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+#pragma unroll
+      for (int q = 0; q < kMaxObstPairs; ++q) acc_ob[m][q] = f2_splat(0.f);
+    }
+  }
+  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&)[C::NOB][3], long long bA, long long bB) {
+    bool near_tie = false;
+    float keep[3];                    // sample A's d/dtheta (planes: stored together with sample B's as one 8-byte store per plane)
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      float t3[3], dth[3], ee[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t3[j] = h ? f2_hi(th[j]) : f2_lo(th[j]);
+      const float x = h ? f2_hi(tx) : f2_lo(tx), y = h ? f2_hi(ty) : f2_lo(ty);
+      near_tie |= eval_single_static<C::NOBS, C::JL, C::GRAD>(p.pu, p.sp, w1, t3, x, y, acc_s, acc_ob, dth, ee, ndiff);
+      const long long b = h ? bB : bA;
+      if (C::GRAD) {
+        if (C::LAYOUT == kPlanes) {
+          if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) keep[j] = dth[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + bA, f2_make(keep[j], dth[j]));
+          }
+        } else {
+          float* d = p.dtheta + b * 3;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[j] = dth[j];
+        }
+      } else {
+        if (p.q_ee) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p.q_ee[b * 3 + c] = ee[c];
+        }
+        if (p.err_sq) {
+          const float ex = x - ee[0], ey = y - ee[1];
+          p.err_sq[b * 2] = 0.5f * (ex * ex);
+          p.err_sq[b * 2 + 1] = 0.5f * (ey * ey);
+        }
+      }
+    }
+    if constexpr (C::GRAD) {
+      if (near_tie) redo_pair_exact<C>(p, w2_plain, bA, bB);
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    float v[C::K];
+    v[0] = acc_s[0];
+    if (C::JL) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[1 + j] = acc_s[1 + j];
+    }
+#pragma unroll
+    for (int o = 0; o < C::NOBS; ++o) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const f2 a = acc_ob[2 - j][o >> 1];
+        v[kObstBase + 3 * o + j] = (o & 1) ? f2_hi(a) : f2_lo(a);
+      }
+    }
+    clear();
+    sacc.flush(v);
   }
   __device__ __forceinline__ void tile_done() {
     if (++since_flush == kFlushSamples / 2) {
@@ -184,8 +313,8 @@ struct StatsBody {
   unsigned cnt[C::K];
   unsigned any_jl, any_ob;
   double err;
-  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);
+  static constexpr bool kPermuted = C::LAYOUT == kRows && C::DYN && C::NOBS == kMaxObst;
+  static constexpr int kObstBase = 1 + (C::JL ? C::J : 0);
   __device__ __forceinline__ StatsBody(const LagrangianParams& pp, int rr) : p(pp), r(rr), any_jl(0), any_ob(0), err(0.0) {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) cnt[i] = 0;
@@ -195,19 +324,19 @@ struct StatsBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) {
       cnt[i] += v[i] > p.stats_threshold;
-      if (C::JL && i >= 1 && i < 4) mjl = fmaxf(mjl, v[i]);
+      if (C::JL && i >= 1 && i < 1 + C::J) mjl = fmaxf(mjl, v[i]);
       if (i >= kObstBase) mob = fmaxf(mob, v[i]);
     }
     any_jl += mjl > 0.f;
     any_ob += mob > 0.f;
     err += (double)__fsqrt_rn(v[0]);      // sqrt(position_err_sq.sum()) with position_err_sq = 0.5*e^2: the reference's |e|/sqrt(2)
   }
-  __device__ __forceinline__ void pair(const f2 (&th)[3], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long, long long) {
-    f2 acc[C::K], dth[3], ee[3];
+  __device__ __forceinline__ void pair(const f2 (&th)[C::J], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long, long long) {
+    f2 acc[C::K], dth[C::J], ee[3];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
     const PackedHostWeights w2{p.pu};
-    eval_pair<C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     float v[C::K];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
@@ -228,10 +357,10 @@ struct StatsBody {
         for (int k = 0; k < 4; ++k) {
           if (k & bit) continue;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const unsigned a = cnt[kObstBase + 3 * k + j], b = cnt[kObstBase + 3 * (k | bit) + j];
-            cnt[kObstBase + 3 * k + j] = sw ? b : a;
-            cnt[kObstBase + 3 * (k | bit) + j] = sw ? a : b;
+          for (int j = 0; j < C::J; ++j) {
+            const unsigned a = cnt[kObstBase + C::J * k + j], b = cnt[kObstBase + C::J * (k | bit) + j];
+            cnt[kObstBase + C::J * k + j] = sw ? b : a;
+            cnt[kObstBase + C::J * (k | bit) + j] = sw ? a : b;
           }
         }
       }
@@ -317,8 +446,8 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
       const unsigned d = dst + h * L::kHalfBytes;
       const int x = b0 + h * kTmaBox;
       tma_load_2d(d, &p.tm_theta, x, 0, bar);
-      tma_load_2d(d + 3 * kTmaBoxBytes, &p.tm_target, x, 0, bar);
-      if (C::DYN) tma_load_3d(d + 5 * kTmaBoxBytes, &p.tm_obst, x, 0, 0, bar);
+      tma_load_2d(d + C::J * kTmaBoxBytes, &p.tm_target, x, 0, bar);
+      if (C::DYN) tma_load_3d(d + (C::J + 2) * kTmaBoxBytes, &p.tm_obst, x, 0, 0, bar);
     }
   };
 
@@ -336,13 +465,13 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
     mbar_wait(bar0 + 8 * stage, parity);
     const long long b = tile * kTmaTile + 2 * tid;
     const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
-    f2 th[3], ob[C::NOB][3];
+    f2 th[C::J], ob[C::NOB][3];
     int pl = 0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
-    const f2 tx = *reinterpret_cast<const f2*>(base + 3 * kTmaBoxBytes);
-    const f2 ty = *reinterpret_cast<const f2*>(base + 4 * kTmaBoxBytes);
-    pl = 5;
+    for (int j = 0; j < C::J; ++j, ++pl) th[j] = *reinterpret_cast<const f2*>(base + pl * kTmaBoxBytes);
+    const f2 tx = *reinterpret_cast<const f2*>(base + C::J * kTmaBoxBytes);
+    const f2 ty = *reinterpret_cast<const f2*>(base + (C::J + 1) * kTmaBoxBytes);
+    pl = C::J + 2;
     if (C::DYN) {
 #pragma unroll
       for (int k = 0; k < C::NOBS; ++k) {
@@ -375,26 +504,48 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
   body.finish();
 }
 
+// Resident blocks per SM the staged kernels are compiled for: the dynamic-obstacle kernels are HBM-bound and run best with
+// 128 registers (2 blocks); the kernels without per-sample obstacles keep fewer values live (no obstacle operands) and are
+// FP32-latency bound, so they trade registers for a third resident block (IKL_STATIC_MIN_BLOCKS).
+#ifndef IKL_STATIC_MIN_BLOCKS
+#define IKL_STATIC_MIN_BLOCKS 2
+#endif
 template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
+constexpr int staged_min_blocks() { return C::DYN ? IKL_MIN_BLOCKS : IKL_STATIC_MIN_BLOCKS; }
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   using L = TmaLayout<C>;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
   __shared__ float2 s_lam2[kMaxK];
   __shared__ double s_warp[kWarps][kMaxK];
+  __shared__ float s_lam1[kMaxK];
+  __shared__ float2 s_lam_pairs[3][kMaxObstPairs];
   if constexpr (C::MODE == kGradDevW) {
     if (threadIdx.x < C::K) {
       const float l = __ldg(p.w_dev + threadIdx.x);
       s_lam2[threadIdx.x] = make_float2(l, l);
+      s_lam1[threadIdx.x] = l;
     }
+    if constexpr (use_single_static<C>()) stage_pair_weights<C>(p.w_dev, &s_lam_pairs[0][0]);
   }
   __shared__ float2 s_ndiff;
   if (threadIdx.x == 0) s_ndiff = p.pu.ob_ndiff;
   WarpSharedAcc<C::K> sacc(s_warp);          // zeroes s_warp; run_planes_pipe starts with a block barrier
   __syncthreads();
   auto run = [&](const auto& w2) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0, &s_ndiff);
-    run_planes_pipe<C>(p, body, dyn_smem, bars);
+    if constexpr (use_single_static<C>()) {
+      auto run1 = [&](const auto& w1) {
+        SingleStaticBody<C, std::decay_t<decltype(w1)>, std::decay_t<decltype(w2)>> body(p, w1, w2, sacc, &s_ndiff);
+        run_planes_pipe<C>(p, body, dyn_smem, bars);
+      };
+      if constexpr (C::MODE == kGradDevW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
+      else run1(SingleHostWeights{p});
+    } else {
+      LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0, &s_ndiff);
+      run_planes_pipe<C>(p, body, dyn_smem, bars);
+    }
   };
   if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
   else run(PackedHostWeights{p.pu});
@@ -410,6 +561,9 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_planes_tm
 // eight lanes of a quarter-warp over all 32 banks.  The thread therefore holds obstacle (k ^ r) in slot k; the maths is
 // symmetric in the obstacles except for the multiplier and the sum each term belongs to: multipliers come from a
 // per-r permuted table in shared memory, sums are put back in order when they are flushed (WarpSharedAcc::flush_xor4).
+// With fewer than four dynamic obstacles (the reference still hands over (B,4,4) rows, kinematics/dataset.py:80-85) the
+// whole tile is staged the same way and slot k simply holds obstacle k (r = 0): the one to three LDS.128 per sample then
+// take 2- to 4-way bank conflicts, i.e. no more shared-memory cycles than the four conflict-free loads of the full case.
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar) : "memory");
@@ -417,14 +571,15 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 
 template <class C>
 struct RowsTmaLayout {
-  static constexpr bool kSupported = C::J == 3 && (!C::DYN || C::NOBS == kMaxObst);
-  static constexpr int kThetaBytes = kTmaTile * 3 * 4;
+  static constexpr bool kSupported = true;
+  static constexpr bool kPermuted = C::DYN && C::NOBS == kMaxObst;         // obstacle (k ^ r) in slot k
+  static constexpr int kThetaBytes = kTmaTile * C::J * 4;
   static constexpr int kTargetBytes = kTmaTile * 3 * 4;                 // room for target rows of 2 or 3 floats
   static constexpr int kObstBytes = C::DYN ? kTmaTile * 4 * kMaxObst * 4 : 0;
   static constexpr int kStageBytes = kThetaBytes + kTargetBytes + kObstBytes;
   static constexpr int kStages = IKL_TMA_STAGES;
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 128;
-  static constexpr int kObstBase = 1 + (C::JL ? 3 : 0);                  // index of the first obstacle constraint
+  static constexpr int kObstBase = 1 + (C::JL ? C::J : 0);              // index of the first obstacle constraint
 };
 
 template <class C, class Body>
@@ -452,7 +607,7 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
     const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
     const unsigned tg_bytes = (unsigned)(kTmaTile * 4) * (unsigned)tg_sb;
     mbar_expect_tx(bar, L::kThetaBytes + tg_bytes + L::kObstBytes);
-    bulk_g2s(dst, p.theta + b0 * 3, L::kThetaBytes, bar);
+    bulk_g2s(dst, p.theta + b0 * C::J, L::kThetaBytes, bar);
     bulk_g2s(dst + L::kThetaBytes, p.target + b0 * tg_sb, tg_bytes, bar);
     if (C::DYN) bulk_g2s(dst + L::kThetaBytes + L::kTargetBytes, p.obst + b0 * (4 * kMaxObst), L::kObstBytes, bar);
   };
@@ -470,11 +625,11 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar0 + 8 * stage, parity);
     const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
-    f2 th[3], ob[C::NOB][3];
-    const float* tA = reinterpret_cast<const float*>(st) + 3 * tid;
-    const float* tB = tA + 3 * kThreads;
+    f2 th[C::J], ob[C::NOB][3];
+    const float* tA = reinterpret_cast<const float*>(st) + C::J * tid;
+    const float* tB = tA + C::J * kThreads;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) th[j] = f2_make(tA[j], tB[j]);
+    for (int j = 0; j < C::J; ++j) th[j] = f2_make(tA[j], tB[j]);
     const float* gA = reinterpret_cast<const float*>(st + L::kThetaBytes) + tg_sb * tid;
     const float* gB = gA + tg_sb * kThreads;
     const f2 tx = f2_make(gA[0], gB[0]);
@@ -517,34 +672,49 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
 }
 
 template <class C>
-__global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
+__global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_rows_tma_kernel(const __grid_constant__ LagrangianParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   using L = RowsTmaLayout<C>;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(dyn_smem + (size_t)L::kStages * L::kStageBytes);
   __shared__ float2 s_lam_perm[4][kMaxK];      // multipliers as (w, w) pairs, obstacle entries permuted by k ^ r
   __shared__ double s_warp[kWarps][kMaxK];
-  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
+  const int r = L::kPermuted ? ((threadIdx.x >> 1) & 3) : 0;
   constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::MODE == kGradDevW);
   if constexpr (kSmemWeights) {
     if (threadIdx.x < 4 * kMaxK) {
       const int rr = threadIdx.x / kMaxK, i = threadIdx.x % kMaxK;
       int src = i;
-      if (C::DYN && i >= L::kObstBase && i < C::K) {
-        const int q = i - L::kObstBase, k = q / 3, j = q % 3;
-        src = L::kObstBase + 3 * (k ^ rr) + j;
+      if (L::kPermuted && i >= L::kObstBase && i < C::K) {
+        const int q = i - L::kObstBase, k = q / C::J, j = q % C::J;
+        src = L::kObstBase + C::J * (k ^ rr) + j;
       }
       float l = 0.f;
       if (i < C::K) l = (C::MODE == kGradDevW) ? __ldg(p.w_dev + src) : p.u.w[src];
       s_lam_perm[rr][i] = make_float2(l, l);
     }
   }
+  __shared__ float s_lam1[kMaxK];
+  __shared__ float2 s_lam_pairs[3][kMaxObstPairs];
+  if constexpr (C::MODE == kGradDevW && use_single_static<C>()) {
+    if (threadIdx.x < C::K) s_lam1[threadIdx.x] = __ldg(p.w_dev + threadIdx.x);
+    stage_pair_weights<C>(p.w_dev, &s_lam_pairs[0][0]);
+  }
   WarpSharedAcc<C::K> sacc(s_warp);            // zeroes s_warp; run_rows_pipe starts with a block barrier
   __shared__ float2 s_ndiff;
   if (threadIdx.x == 0) s_ndiff = p.pu.ob_ndiff;
   __syncthreads();
   auto run = [&](const auto& w2, const auto& w2_plain) {
-    LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r, &s_ndiff);
-    run_rows_pipe<C>(p, body, dyn_smem, bars, r);
+    if constexpr (use_single_static<C>()) {
+      auto run1 = [&](const auto& w1) {
+        SingleStaticBody<C, std::decay_t<decltype(w1)>, std::decay_t<decltype(w2_plain)>> body(p, w1, w2_plain, sacc, &s_ndiff);
+        run_rows_pipe<C>(p, body, dyn_smem, bars, r);
+      };
+      if constexpr (C::MODE == kGradDevW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
+      else run1(SingleHostWeights{p});
+    } else {
+      LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r, &s_ndiff);
+      run_rows_pipe<C>(p, body, dyn_smem, bars, r);
+    }
   };
   if constexpr (kSmemWeights) run(PackedSmemWeights{s_lam_perm[r]}, PackedSmemWeights{s_lam_perm[0]});     // table 0: k ^ 0 = k
   else run(PackedHostWeights{p.pu}, PackedHostWeights{p.pu});
@@ -556,10 +726,10 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) lagrangian_rows_tma_
     for (int i = 0; i < C::K; ++i) sacc1[i] = 0.f;
     auto tail = [&](const auto& w) {
       for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
-        float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3];
+        float th[C::J], tx, ty, ob[C::NOB][3], dth[C::J], ee[3];
         if (!C::DYN) static_obstacles<C>(p, ob);
         load_sample<C>(p, b, th, tx, ty, ob);
-        eval_sample<3, C::NOBS, C::JL, C::GRAD, true>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
+        eval_sample<C::J, C::NOBS, C::JL, C::GRAD, C::UNIT>(p.u, w, th, tx, ty, ob, sacc1, dth, ee);
         store_sample<C>(p, b, dth, ee, tx, ty);
       }
     };
@@ -595,19 +765,19 @@ __global__ void __launch_bounds__(kThreads, IKL_MIN_BLOCKS) stats_rows_tma_kerne
   __shared__ unsigned s_counts[kStatSlots];
   __shared__ double s_err[kWarps];
   if (threadIdx.x < kStatSlots) s_counts[threadIdx.x] = 0;
-  const int r = C::DYN ? ((threadIdx.x >> 1) & 3) : 0;
+  const int r = L::kPermuted ? ((threadIdx.x >> 1) & 3) : 0;
   StatsBody<C> body(p, r);
   run_rows_pipe<C>(p, body, dyn_smem, bars, r);
   // ragged tail (< 512 rows), one sample per thread through the scalar code
   const long long full = (p.batch / kTmaTile) * kTmaTile;
   const HostWeights w(p.u, nullptr);
   for (long long b = full + (long long)blockIdx.x * kThreads + threadIdx.x; b < p.batch; b += (long long)gridDim.x * kThreads) {
-    float th[3], tx, ty, ob[C::NOB][3], dth[3], ee[3], acc[C::K];
+    float th[C::J], tx, ty, ob[C::NOB][3], dth[C::J], ee[3], acc[C::K];
     if (!C::DYN) static_obstacles<C>(p, ob);
     load_sample<C>(p, b, th, tx, ty, ob);
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = 0.f;
-    eval_sample<3, C::NOBS, C::JL, false, true>(p.u, w, th, tx, ty, ob, acc, dth, ee);
+    eval_sample<C::J, C::NOBS, C::JL, false, C::UNIT>(p.u, w, th, tx, ty, ob, acc, dth, ee);
     body.add(acc);
   }
   body.commit(s_counts, s_err);

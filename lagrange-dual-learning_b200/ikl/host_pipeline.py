@@ -22,16 +22,8 @@ class HostLagrangianPipeline(object):
     self.chunk = int(chunk)
     self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     self.n_buffers = n_buffers
-    J, dev, C = spec.num_links, self.device, self.chunk
-    self.bufs = []
-    for _ in range(n_buffers):
-      self.bufs.append({
-          "theta": torch.empty(C, J, dtype=torch.float32, device=dev),
-          "q_des": torch.empty(C, 3, dtype=torch.float32, device=dev),
-          "obst": torch.empty(C, 4, 4, dtype=torch.float32, device=dev) if spec.dynamic else None,
-          "dtheta": torch.empty(C, J, dtype=torch.float32, device=dev),
-          "ready": torch.cuda.Event(), "computed": torch.cuda.Event(), "drained": torch.cuda.Event(),
-      })
+    self.bufs = None
+    self._buf_shapes = None
     self.s_in = torch.cuda.Stream(dev)
     self.s_compute = torch.cuda.Stream(dev)
     self.s_out = torch.cuda.Stream(dev)
@@ -40,12 +32,32 @@ class HostLagrangianPipeline(object):
     self.h2d_bytes = 0
     self.d2h_bytes = 0
 
+  def _staging(self, q_cols, obst_shape):
+    """Device staging buffers in the shapes of the host tensors: the reference's (B,3) targets / (B,4,4) obstacle rows, or
+    the compact (B,2) / (B,n,3) forms that carry only what the path reads (68 instead of 88 bytes per sample over PCIe)."""
+    shapes = (q_cols, obst_shape)
+    if self._buf_shapes != shapes:
+      J, dev, C = self.spec.num_links, self.device, self.chunk
+      self.bufs = []
+      for _ in range(self.n_buffers):
+        self.bufs.append({
+            "theta": torch.empty(C, J, dtype=torch.float32, device=dev),
+            "q_des": torch.empty(C, q_cols, dtype=torch.float32, device=dev),
+            "obst": torch.empty((C,) + tuple(obst_shape), dtype=torch.float32, device=dev) if self.spec.dynamic else None,
+            "dtheta": torch.empty(C, J, dtype=torch.float32, device=dev),
+            "ready": torch.cuda.Event(), "computed": torch.cuda.Event(), "drained": torch.cuda.Event(),
+        })
+      self._buf_shapes = shapes
+    return self.bufs
+
   def run(self, theta, q_ee_desired, obstacles, lam, dtheta_out):
     """All tensors are HOST tensors (pinned for full overlap).  lam: K host floats.  Returns (viol (K,) f64 host, loss float).
 
-    dtheta_out (B,J) host tensor receives the gradient.  The call returns after everything has landed on the host.
+    q_ee_desired (B,3) or (B,2); obstacles (B,4,4) rows [x,y,r,pad] as the reference's DataLoader hands them, or compact
+    (B,n_obs,3).  dtheta_out (B,J) host tensor receives the gradient.  The call returns after everything has landed on the host.
     """
     spec, C = self.spec, self.chunk
+    self._staging(q_ee_desired.shape[1], tuple(obstacles.shape[1:]) if spec.dynamic else ())
     B = theta.shape[0]
     lam_list = [float(v) for v in (lam.tolist() if isinstance(lam, torch.Tensor) else lam)]
     cur = torch.cuda.current_stream(self.device)
@@ -65,7 +77,7 @@ class HostLagrangianPipeline(object):
         self.h2d_bytes += n * (theta.shape[1] + q_ee_desired.shape[1]) * 4
         if spec.dynamic:
           buf["obst"][:n].copy_(obstacles[start:start + n], non_blocking=True)
-          self.h2d_bytes += n * 64
+          self.h2d_bytes += n * obstacles[0].numel() * 4
         buf["ready"].record(self.s_in)
       with torch.cuda.stream(self.s_compute):
         self.s_compute.wait_event(buf["ready"])

@@ -40,6 +40,7 @@ def lib():
     _lib.ik_oracle_num_constraints.argtypes = [ctypes.POINTER(OracleSpecC)]
     _lib.ik_oracle_lagrangian_f64.argtypes = [ctypes.POINTER(OracleSpecC), ctypes.c_longlong] + [ctypes.c_void_p] * 7
     _lib.ik_oracle_lagrangian_f32.argtypes = [ctypes.POINTER(OracleSpecC), ctypes.c_longlong] + [ctypes.c_void_p] * 6
+    _lib.ik_oracle_diagnostics_f64.argtypes = [ctypes.POINTER(OracleSpecC), ctypes.c_longlong] + [ctypes.c_void_p] * 8
   return _lib
 
 
@@ -92,6 +93,24 @@ def lagrangian_f32(ospec, theta, q_des, obst, weights, want_grad=True):
                                   w.ctypes.data, sums.ctypes.data, dth.ctypes.data if want_grad else None)
   assert rc == 0
   return sums, dth
+
+
+def diagnostics_f64(ospec, theta, q_des, obst, weights, want_terms=False):
+  """Per-sample float64 diagnostics (see ik_oracle_diagnostics_f64): dict with kink_dist (B,), cond (B,), tips (B,6) and,
+  if requested, terms (B,K)."""
+  L, s = lib(), c_spec(ospec)
+  K = L.ik_oracle_num_constraints(ctypes.byref(s))
+  th, qd = _f32(theta), _f32(q_des)
+  ob = _f32(obst) if (ospec.dynamic and obst is not None) else None
+  B = th.shape[0]
+  w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+  kink, cond, tips = np.zeros(B), np.zeros(B), np.zeros((B, 6))
+  terms = np.zeros((B, K)) if want_terms else None
+  rc = L.ik_oracle_diagnostics_f64(ctypes.byref(s), B, th.ctypes.data, qd.ctypes.data, ob.ctypes.data if ob is not None else None,
+                                   w.ctypes.data, kink.ctypes.data, cond.ctypes.data, tips.ctypes.data,
+                                   terms.ctypes.data if want_terms else None)
+  assert rc == 0
+  return {"kink_dist": kink, "cond": cond, "tips": tips, "terms": terms}
 
 
 def max_threads():

@@ -194,3 +194,51 @@ int ik_oracle_lagrangian_f32(const OracleSpecC* s, long long B, const float* the
   for (int k = 0; k < K; ++k) sums[k] = tot[k];
   return 0;
 }
+
+/* Per-sample diagnostics in double precision for tools/parity_report.py (any output may be NULL):
+ *   kink_dist[b]  min over the penalty terms (everything but the end-effector term) of |term|: how close the sample sits to
+ *                 a kink of a piecewise-linear penalty, where a 1-ulp difference legitimately flips the subgradient
+ *                 (the GPU tests mask |term| < 1e-6); +infinity when the config has no penalty terms
+ *   cond[b]       sum over the obstacle terms of |w_i| * max(slope) / d_i: the lever arm by which the unit vector (p - c)/d
+ *                 amplifies the ~1e-7 round-off any fp32 forward kinematics carries into the gradient
+ *   tips[b][6]    (p3x, p3y, p2x, p2y, p1x, p1y)  -- end effector first, like the FK tuple
+ *   terms[b][K]   the K per-sample constraint terms */
+int ik_oracle_diagnostics_f64(const OracleSpecC* s, long long B, const float* theta, const float* target, const float* obst,
+                              const double* w, double* kink_dist, double* cond, double* tips, double* terms_out) {
+  const int K = num_constraints(s);
+  if (K > MAXK || (s->dynamic && s->num_obstacles > 0 && !obst)) return 1;
+  const double hi = s->good_slope > s->bad_slope ? s->good_slope : s->bad_slope;
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < B; ++i) {
+    double terms[MAXK];
+    sample_f64(s, theta + 3 * i, target + 3 * i, obst ? obst + 16 * i : NULL, w, terms, NULL);
+    if (terms_out) for (int k = 0; k < K; ++k) terms_out[(size_t)i * K + k] = terms[k];
+    if (kink_dist) {
+      double m = INFINITY;
+      for (int k = 1; k < K; ++k) m = fabs(terms[k]) < m ? fabs(terms[k]) : m;
+      kink_dist[i] = m;
+    }
+    if (cond || tips) {
+      const double t0 = theta[3 * i], t1 = t0 + theta[3 * i + 1], t2 = t1 + theta[3 * i + 2];
+      double px[3], py[3];
+      px[0] = cos(t0); py[0] = sin(t0);
+      px[1] = px[0] + cos(t1); py[1] = py[0] + sin(t1);
+      px[2] = px[1] + cos(t2); py[2] = py[1] + sin(t2);
+      if (tips) for (int j = 0; j < 3; ++j) { tips[6 * i + 2 * j] = px[2 - j]; tips[6 * i + 2 * j + 1] = py[2 - j]; }
+      if (cond) {
+        double c = 0.0;
+        int idx = 1 + (s->enforce_joint_limits ? 3 : 0);
+        for (int o = 0; o < s->num_obstacles; ++o) {
+          const float* ob = s->dynamic ? obst + 16 * i + 4 * o : s->static_obstacles[o];
+          for (int j = 0; j < 3; ++j, ++idx) {
+            const double dx = px[2 - j] - (double)ob[0], dy = py[2 - j] - (double)ob[1];
+            const double d = sqrt(dx * dx + dy * dy);
+            c += fabs(w[idx]) * hi / (d > 1e-12 ? d : 1e-12);
+          }
+        }
+        cond[i] = c;
+      }
+    }
+  }
+  return 0;
+}

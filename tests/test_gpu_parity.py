@@ -73,13 +73,19 @@ def oracle_truth(ospec, theta, q_des, obst, lam):
 
 
 def grad_close(got, ref, truth, scale=None):
-  """Per-sample gradient comparison away from kinks, with the conditioning-aware bound described in oracle_truth."""
+  """Per-sample gradient comparison away from kinks.  The plain bound is the north_star one, 1e-5 * S.  Measured at 2^24
+  samples on the B200 (profiles/r02/parity_report.json): 99.99 % of the samples are within 2.2e-6 * S and 3 to 4 per
+  MILLION exceed 1e-5 * S -- the ones whose tip lies almost on a circle centre, where the unit vector (p - c)/d amplifies
+  the ~1e-7 round-off any fp32 FK carries.  So at most 2e-5 of the unmasked samples (and never more than a handful of a small
+  batch) may use the conditioning-aware bound of oracle_truth; everything else must meet 1e-5 * S."""
   got = np.asarray(got, dtype=np.float64)
   ref = np.asarray(ref, dtype=np.float64)
   keep = ~truth.kink
   s = float(np.max(np.abs(ref))) if scale is None else float(scale)
-  bound = RTOL * s + 3e-6 * truth.cond
   err = np.abs(got - ref).max(axis=1)
+  plain_bad = keep & (err > RTOL * s)
+  assert plain_bad.sum() <= max(2, 2e-5 * keep.sum()), "d/dtheta beyond 1e-5*S at %d of %d samples" % (plain_bad.sum(), keep.sum())
+  bound = RTOL * s + 3e-6 * truth.cond
   bad = keep & (err > bound)
   assert not bad.any(), "d/dtheta off at %d samples, worst %.3e (bound %.3e)" % (bad.sum(), err[bad].max(), bound[bad][err[bad].argmax()])
   assert truth.kink.mean() < 3e-3 or len(got) < 1000
@@ -889,41 +895,52 @@ def test_layout_dispatch_on_views_and_alignments(cuda_device, monkeypatch):
   assert float((sums - v0).abs().max()) <= 1e-6 * float(v0.abs().max())
 
 
+@pytest.mark.parametrize("name", ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static", "cfg_no_constraints"))
 @pytest.mark.parametrize("J,lengths", [(2, (1.0, 1.0)), (3, (0.7, 1.3, 0.45)), (2, (0.5, 1.5))])
-def test_two_links_and_non_unit_link_lengths(J, lengths, cuda_device):
-  """The strided kernel family: 2-link arms (reference: only the NumPy FK, forward_kinematics.py:7-22) and runtime link
-  lengths (utils/constants.py holds them as constants), against the oracle evaluated with the same geometry."""
+def test_two_links_and_non_unit_link_lengths(J, lengths, name, cuda_device, monkeypatch):
+  """2-link arms (reference: only the NumPy FK, forward_kinematics.py:7-22; BASELINE config 1 names two_link_arm) and runtime
+  link lengths (utils/constants.py:1-13 holds them as constants) run on the same packed / staged kernels as the 3-link unit
+  arm -- rows, planes and the strided fallback -- against the oracle evaluated with the same geometry."""
   import dataclasses
   from ikl import ConstraintSpec, fused, _cabi
-  cfg = config_json("cfg_joint_limits_and_4obs_dynamic")
+  cfg = config_json(name)
   spec = ConstraintSpec.from_config(cfg, J, 0.005, 1.0, link_lengths=lengths)
   ospec = dataclasses.replace(O.spec_from_json(cfg, J, 0.005, 1.0), link_lengths=tuple(lengths))
   K = spec.num_constraints
-  assert K == 1 + J + 4 * J == ospec.num_constraints
+  assert K == ospec.num_constraints == 1 + (J if cfg["enforce_joint_limits"] else 0) + J * spec.num_obstacles
   g = torch.Generator().manual_seed(40 + J)
-  B = 3000
+  B = 3000                                           # 5 full 512-sample tiles + a ragged one
   theta = (torch.rand(B, J, generator=g) * 2 - 1) * 2.5
   q_des = torch.cat([(torch.rand(B, 2, generator=g) * 2 - 1) * sum(lengths), torch.zeros(B, 1)], dim=1)
   obst = torch.zeros(B, 4, 4)
   obst[:, :, :2] = (torch.rand(B, 4, 2, generator=g) * 2 - 1) * 1.2
   obst[:, :, 2] = 0.4
   lam = np.linspace(0.4, 1.9, K).astype(np.float32)
-  ref = O.lagrangian(theta.double(), q_des.double(), torch.from_numpy(lam).double(), ospec, obst.double(), per_sample=True)
+  ref = O.lagrangian(theta.double(), q_des.double(), torch.from_numpy(lam).double(), ospec, obst.double() if ospec.dynamic else None,
+                     per_sample=True)
   sums64 = ref["constraint_violations"].numpy()
   abs_sums = ref["per_sample_terms"].abs().sum(dim=0).numpy()
-  _, dth64 = O.lagrangian_grad_closed_form(theta.numpy(), q_des.numpy(), lam, ospec, obst.numpy())
-  dev = cuda_device
-  viol, loss, dth = fused.lagrangian_forward_backward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam.tolist())
-  assert "<strided,J%d" % J in _cabi.last_kernel_name()
-  assert np.all(np.abs(viol.cpu().numpy() - sums64) <= RTOL * abs_sums)
-  err = np.abs(dth.cpu().numpy() - dth64).max(axis=1)
+  _, dth64 = O.lagrangian_grad_closed_form(theta.numpy(), q_des.numpy(), lam, ospec, obst.numpy() if ospec.dynamic else None)
   scale = np.abs(dth64).max()
-  assert (err > RTOL * scale).mean() < 3e-3 and err.max() < 1e-3 * scale      # see oracle_truth on conditioning
-  # forward-only launch and the function-level FK agree with the same geometry
-  out = fused.lagrangian_forward(spec, theta.to(dev), q_des.to(dev), obst.to(dev), lam.tolist(), want_q_ee=(J == 3))
-  assert np.array_equal(out["constraint_violations"].cpu().numpy(), viol.cpu().numpy())
+  tag = "J%d" % J
+  unit = "unit" if (J == 3 and all(v == 1.0 for v in lengths)) else "len"
+  grads = {}
+  for layout, want in (("rows", "rows_tma"), ("planes", "planes_tma"), ("strided", "<strided")):
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(cuda_device)):
+      viol, loss, dth, kname = run_layout(layout, spec, theta, q_des, obst, weights, True, monkeypatch)
+      assert want in kname and tag in kname and (layout == "strided" or unit in kname), kname
+      assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums + 1e-30), (layout, kname)
+      err = np.abs(dth - dth64).max(axis=1)
+      assert (err > RTOL * scale).mean() < 3e-3 and err.max() < 1e-3 * scale, (layout, kname)      # see oracle_truth on conditioning
+    grads[layout] = dth
+    viol_f, _, _, _ = run_layout(layout, spec, theta, q_des, obst, lam.tolist(), False, monkeypatch)
+    assert np.array_equal(viol_f, viol), "forward-only and fused fwd+bwd launches must give identical sums"
+  for layout in ("rows", "strided"):
+    assert float(np.abs(grads[layout] - grads["planes"]).max()) <= 2e-6 * scale
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  # the function-level FK agrees with the same geometry
   from ikl import ops
-  tips = ops.fk_forward_kinematics(theta.to(dev), lengths)
+  tips = ops.fk_forward_kinematics(theta.to(cuda_device), lengths)
   close(tips[0].cpu().numpy(), O.forward_kinematics(theta.double(), lengths)[0].numpy(), scale=sum(lengths))
 
 

@@ -23,7 +23,9 @@ def measure(args):
   from ikl import ConstraintSpec, standard_config, fused, synthetic, _cabi
   dev = torch.device("cuda:0")
   B = 1 << args.batch_log2
-  theta, q_des, obst = synthetic.make_batch(B, seed=0, device="cuda:0")
+  J = args.num_links
+  lengths = tuple(float(v) for v in args.link_lengths.split(",")) if args.link_lengths else None
+  theta, q_des, obst = synthetic.make_batch(B, seed=0, device="cuda:0", num_links=J)
   planes = synthetic.to_planes(theta, q_des, obst)
   rows = (theta, q_des, obst)
   peak = 6548.8
@@ -31,14 +33,17 @@ def measure(args):
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
   except Exception:
     pass
-  cases = [("cfg_joint_limits_and_4obs_dynamic", 80, 68), ("cfg_joint_limits_and_4obs_static", 32, 20),
-           ("cfg_joint_limits_and_1obs_static", 32, 20), ("cfg_joint_limits", 32, 20), ("cfg_no_constraints", 32, 20)]
+  # algorithmic bytes per sample (generalised to J links): theta 4J + target 8 (+ 4 obstacles x 12) in, dtheta 4J out
+  dyn_f, stat_f = 4 * J + 8 + 48, 4 * J + 8
+  cases = [("cfg_joint_limits_and_4obs_dynamic", dyn_f + 4 * J, dyn_f), ("cfg_joint_limits_and_4obs_static", stat_f + 4 * J, stat_f),
+           ("cfg_joint_limits_and_1obs_static", stat_f + 4 * J, stat_f), ("cfg_joint_limits", stat_f + 4 * J, stat_f),
+           ("cfg_no_constraints", stat_f + 4 * J, stat_f)]
   if args.quick:
     cases = cases[:1]
   if args.configs:
     cases = [c for c in cases if any(c[0].endswith(n) for n in args.configs.split(","))]
   for cfg_name, bytes_fb, bytes_f in cases:
-    spec = ConstraintSpec.from_config(standard_config(cfg_name), 3, 0.005, 1.0)
+    spec = ConstraintSpec.from_config(standard_config(cfg_name), J, 0.005, 1.0, link_lengths=lengths)
     K = spec.num_constraints
     lam = [1.0 + 0.1 * i for i in range(K)]
     lam_dev = torch.tensor(lam, device=dev)
@@ -69,7 +74,8 @@ def measure(args):
           best = min(best, ms)
           tot += ms
         nbytes = bytes_f if mode == "fwd" else bytes_fb
-        print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "config": cfg_name, "layout": lname, "mode": mode,
+        print(json.dumps({"lib": os.path.basename(_cabi.loaded_path()), "config": cfg_name, "links": J, "layout": lname, "mode": mode,
+                          "algorithmic_bytes_per_sample": nbytes,
                           "kernel": _cabi.last_kernel_name(), "ms_mean": round(tot / 3, 4), "ms_best": round(best, 4),
                           "gsamples_per_s": round(B / best / 1e6, 2), "algo_GBps": round(nbytes * B / best / 1e6, 1),
                           "frac_of_hbm_peak": round(nbytes * B / best / 1e6 / peak, 4)}), flush=True)
@@ -169,11 +175,13 @@ def main():
   ap.add_argument("--quick", action="store_true")
   ap.add_argument("--configs", default="", help="comma-separated config-name suffixes to keep, e.g. 4obs_static,no_constraints")
   ap.add_argument("--layouts", default="", help="planes and/or rows")
+  ap.add_argument("--num-links", type=int, default=3, choices=[2, 3])
+  ap.add_argument("--link-lengths", default="", help="comma-separated link lengths (default: unit lengths)")
   ap.add_argument("--child", action="store_true")
   args = ap.parse_args()
   if args.child or not args.libs:
     measure(args)
-    if not args.quick and not args.configs and not args.layouts:
+    if not args.quick and not args.configs and not args.layouts and args.num_links == 3 and not args.link_lengths:
       measure_elementwise(args)
       measure_callers(args)
     return
@@ -186,6 +194,9 @@ def main():
       cmd += ["--configs", args.configs]
     if args.layouts:
       cmd += ["--layouts", args.layouts]
+    cmd += ["--num-links", str(args.num_links)]
+    if args.link_lengths:
+      cmd += ["--link-lengths", args.link_lengths]
     subprocess.run(cmd, env=env, check=False)
 
 
