@@ -88,7 +88,10 @@ def _build_locked(force, variant, defines, verbose):
   if not force and os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
     return out
   nvcc = nvcc_path()
-  obj_dir = os.path.join(PKG_DIR, "build", "obj_" + (variant or "default"))
+  # objects live outside the tree (they are large and must not travel with the gpurun snapshot; only lib/*.so does)
+  import tempfile
+  base = os.environ.get("IKL_BUILD_DIR") or os.path.join(tempfile.gettempdir(), "ikl_build_" + hashlib.sha1(PKG_DIR.encode()).hexdigest()[:10])
+  obj_dir = os.path.join(base, "obj_" + (variant or "default"))
   os.makedirs(obj_dir, exist_ok=True)
   jobs = [(nvcc, s, os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o"), tuple(defines)) for s in _sources()]
   logs = []

@@ -24,6 +24,7 @@ class HostLagrangianPipeline(object):
     self.n_buffers = n_buffers
     self.bufs = None
     self._buf_shapes = None
+    dev = self.device
     self.s_in = torch.cuda.Stream(dev)
     self.s_compute = torch.cuda.Stream(dev)
     self.s_out = torch.cuda.Stream(dev)

@@ -177,6 +177,7 @@ def main():
   ap.add_argument("--layouts", default="", help="planes and/or rows")
   ap.add_argument("--num-links", type=int, default=3, choices=[2, 3])
   ap.add_argument("--link-lengths", default="", help="comma-separated link lengths (default: unit lengths)")
+  ap.add_argument("--repeat", type=int, default=1, help="with --libs: cycle through the list this many times (take the best per lib)")
   ap.add_argument("--child", action="store_true")
   args = ap.parse_args()
   if args.child or not args.libs:
@@ -185,7 +186,7 @@ def main():
       measure_elementwise(args)
       measure_callers(args)
     return
-  for lib in args.libs.split(","):
+  for lib in args.libs.split(",") * max(1, args.repeat):     # --repeat: A B C A B C ... so that clock drift hits every lib alike
     env = dict(os.environ, IKL_LIB=os.path.join(PKG, "lib", lib) if not os.path.isabs(lib) else lib)
     cmd = [sys.executable, os.path.abspath(__file__), "--child", "--batch-log2", str(args.batch_log2), "--iters", str(args.iters)]
     if args.quick:

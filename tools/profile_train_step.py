@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel-level breakdown of one large-batch train step (torch.profiler): SimpleNetwork forward (cuBLAS), the fused
-Lagrangian, backward, Adam.  python tools/profile_train_step.py [log2 batch=20]"""
+Lagrangian, backward, Adam -- the micro-step bench.py's train_step metric repeats (planes data, last layer transposed,
+no gradient rescaling pass).  python tools/profile_train_step.py [log2 batch=20] [output file]"""
 import os
 import sys
 
@@ -23,13 +24,15 @@ opt = torch.optim.Adam(model.parameters(), lr=5e-5, betas=(0.9, 0.999))
 theta0, q_des, obst = synthetic.make_batch(B, seed=1000, device="cuda:0")
 x = torch.zeros(B, 20, device=dev)
 x[:, 0:2] = q_des[:, :2]
+x[:, 2], x[:, 3] = -synthetic.LIMIT, synthetic.LIMIT
 x[:, 4:] = obst.reshape(B, 16)
+_, q_pl, ob_pl = synthetic.to_planes(theta0, q_des, obst)
 lam_dev = torch.tensor(lam, device=dev)
 
 
 def step():
-  theta = model(x)
-  viol, loss = fused.FusedIkLagrangian.apply(theta, q_des, obst, lam_dev, spec, lam)
+  theta = model.forward_planes(x)
+  viol, loss = fused.FusedIkLagrangian.apply(theta, q_pl, ob_pl, lam_dev, spec, lam, True)
   model.zero_grad()
   loss.backward()
   opt.step()
@@ -42,4 +45,10 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
   for _ in range(3):
     step()
   torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+table = prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70)
+print(table)
+if len(sys.argv) > 2:
+  with open(sys.argv[2], "w") as f:
+    f.write("torch.profiler, 3 train steps of %d samples (SimpleNetwork 20->100x8->3 fp32 on cuBLAS, fused IK Lagrangian, Adam) on %s\n" % (
+        B, torch.cuda.get_device_name(0)))
+    f.write(table + "\n")
