@@ -218,6 +218,29 @@ def reference_tree_samples_per_s(batch_log2, steps, warmup):
   return B / dt, dt, torch.get_num_threads(), B
 
 
+def parity_summary():
+  """Measured parity of the benchmarked kernels against the float64 oracle at 2^24 samples (tools/parity_report.py, run on the
+  B200 and committed as profiles/r02/parity_report.json) -- numbers, not a pass/fail flag; the tests enforce the tolerances."""
+  path = os.path.join(ROOT, "profiles", "r02", "parity_report.json")
+  try:
+    with open(path) as f:
+      rep = json.load(f)
+    c5 = rep["configs"][CONFIG_NAME]["planes"]
+    worst_sum = max(rep["configs"][n][l]["sums_max_rel_to_sum_abs_terms"] for n in rep["configs"] for l in ("planes", "rows"))
+    return {"source": "profiles/r02/parity_report.json (tools/parity_report.py, float64 oracle, 2^24 samples, all five configs)",
+            "tolerance": "1e-5 relative (north_star)",
+            "positions_max_rel_to_reach": rep["positions"]["max_rel_to_reach_3"],
+            "penalties_max_rel": max(rep["penalties"]["joint_limit_max_rel_to_max_ref"], rep["penalties"]["circle_max_rel_to_max_ref"]),
+            "dtheta_p99_99_rel": c5["dtheta_p99_99_rel_away_from_kinks"], "dtheta_max_rel_away_from_kinks": c5["dtheta_max_rel_away_from_kinks"],
+            "dtheta_fraction_beyond_1e-5": c5["fraction_above_1e-5_S_away_from_kinks"],
+            "dtheta_fraction_beyond_conditioning_bound": c5["fraction_above_conditioning_bound"],
+            "kink_fraction_masked": rep["configs"][CONFIG_NAME]["kink_fraction"],
+            "sums_max_rel_to_sum_abs_terms_all_configs": worst_sum,
+            "lambda_after_12_dual_steps_rel": rep["lambda_after_12_dual_steps"]["max_rel_err"]}
+  except Exception as e:
+    return {"unavailable": str(e)[:200]}
+
+
 def cpu_baseline_leg(args):
   """cpu_baseline of the ours arm: the reference's own code from baseline/_ref in a fresh process (so that its `kinematics`
   package, not this repo's drop-in, is the one imported) on a bounded 2^cpu_batch_log2 sample; the oracle port in-process
@@ -822,6 +845,7 @@ def run_ours(args):
 
   if rank == 0:
     line["e2e"] = e2e
+    line["parity"] = parity_summary()
     line["train_step"] = train
     line["multi_gpu_check"] = multi_check
     line["strong_scaling"] = strong

@@ -602,6 +602,39 @@ def test_random_configurations_every_layout(seed, cuda_device, monkeypatch):
     assert abs(float(err) - want_err) <= 1e-5 * want_err
 
 
+@pytest.mark.parametrize("nobs", [1, 2, 3])
+def test_staged_rows_kernel_with_fewer_than_four_dynamic_obstacles(nobs, cuda_device, monkeypatch):
+  """The reference hands (B,4,4) obstacle rows over whatever random_obstacles_num is (kinematics/dataset.py:80-85); with 1-3
+  dynamic obstacles the bulk-copy staged rows kernel still applies (round 1: direct-load fallback) and reads obstacle k from
+  slot k -- same sums and gradient as the planes kernel and the oracle."""
+  from ikl import ConstraintSpec, synthetic
+  from ikl.configs import make_config
+  cfg = make_config((-2.094395, 2.094395), num_dynamic=nobs)
+  spec, ospec = ConstraintSpec.from_config(cfg, 3, 0.005, 1.0), O.spec_from_json(cfg, 3, 0.005, 1.0)
+  K = spec.num_constraints
+  assert K == 4 + 3 * nobs
+  B = 5 * 512 + 77
+  theta, q_des, obst = synthetic.make_batch(B, seed=300 + nobs)
+  obst[:, nobs:, :] = float("nan")                       # rows the configuration does not use must never be read into the result
+  lam = np.linspace(0.3, 2.1, K).astype(np.float32)
+  clean = obst.clone()
+  clean[:, nobs:, :] = 0.0
+  sums64, abs_sums, dth64, kink, truth = oracle_truth(ospec, theta, q_des, clean, lam)
+  out = {}
+  for layout in ("rows", "planes"):
+    ob_in = obst if layout == "rows" else clean
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(cuda_device)):
+      viol, loss, dth, kname = run_layout(layout, spec, theta if layout == "rows" else theta[:B - 1], q_des if layout == "rows" else q_des[:B - 1],
+                                          ob_in if layout == "rows" else ob_in[:B - 1], weights, True, monkeypatch)
+      assert (layout + "_tma,J3,obs%d,dyn" % nobs) in kname, kname
+      if layout == "rows":
+        assert np.all(np.isfinite(viol)) and np.all(np.isfinite(dth))
+        assert np.all(np.abs(viol - sums64) <= RTOL * abs_sums)
+        grad_close(dth, dth64, truth)
+    out[layout] = dth
+  assert float(np.abs(out["rows"][:B - 1] - out["planes"]).max()) <= 2e-6 * float(np.abs(dth64).max())
+
+
 def test_tie_and_singularity_conventions(cuda_device, monkeypatch):
   """theta exactly at a limit / at mid-range, a tip exactly on a circle, a tip exactly on a centre."""
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
