@@ -167,3 +167,57 @@ def test_in_kernel_peer_exchange_of_the_sums(tmp_path):
   s.close()
   mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
   assert (tmp_path / "ex_ok_0").exists() and (tmp_path / "ex_ok_1").exists()
+
+
+def _graph_worker(rank, world, port, tmpdir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  for p in (ROOT, FUSED_OVERLAY, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  try:
+    import pathlib
+    from test_gpu_trainer import make_trainer
+    fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % NAME))
+    trainers = []
+    for tag, extra in (("eager", ()), ("graph", ("--cuda_graph",))):
+      d = pathlib.Path(tmpdir) / ("%s_rank%d" % (tag, rank))
+      d.mkdir(parents=True, exist_ok=True)
+      tr = make_trainer(NAME, d, fx, extra=extra)
+      if tag == "graph":
+        tr.optimizer = torch.optim.Adam(tr.model.parameters(), lr=tr.opt.optimizer_lr, betas=(0.9, 0.999), capturable=True)
+        assert tr.use_graph and tr.world == world
+      trainers.append(tr)
+    for tr in trainers:
+      for _ in range(3):
+        tr.train_with_relaxation(tr.lambda_multipliers)
+        tr.lambda_multipliers = tr.update_multipliers(tr.lambda_multipliers)
+    eager, graph = trainers
+    assert graph._graph_step is not None and graph._graph_step.batch_size == 64 // world
+    assert float((eager.lambda_multipliers - graph.lambda_multipliers).abs().max()) <= 1e-5 * float(eager.lambda_multipliers.abs().max())
+    for a, b in zip(eager.model.parameters(), graph.model.parameters()):
+      assert float((a - b).detach().abs().max()) <= 2e-5 * max(1.0, float(a.detach().abs().max()))
+    flat = torch.cat([graph.lambda_multipliers.reshape(-1)] + [p.detach().reshape(-1) for p in graph.model.parameters()])
+    flats = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(flats, flat)
+    assert all(torch.equal(f, flats[0]) for f in flats), "graph replicas must stay in lock-step"
+    want = fx["lambda_history"][3].to(flat.device)
+    assert float((graph.lambda_multipliers - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    open(os.path.join(tmpdir, "graph_ok_%d" % rank), "w").write("ok")
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_cuda_graph_step_captures_the_gradient_all_reduce(tmp_path):
+  """--cuda_graph under torch.distributed: forward, fused Lagrangian, backward, the flat NCCL all-reduce of the gradients and
+  Adam are ONE graph replay per step on every rank; same lambda / weights as the eager two-rank run and as the reference's
+  single-process run on the same global batches."""
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  mp.spawn(_graph_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert (tmp_path / "graph_ok_0").exists() and (tmp_path / "graph_ok_1").exists()
