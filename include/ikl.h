@@ -130,7 +130,8 @@ IklStatus ikl_lagrangian_forward_backward(const IklSpec* spec, const IklBatch* i
  * The reference has no distributed code; the path shards because every constraint value is a SUM over samples
  * (scripts/trainer.py:195,204,239).  With one process per GPU, each rank runs the fused kernel on its shard; the block that
  * finishes a rank's reduction stores that rank's K double-precision sums straight into every peer's mailbox (NVLink P2P
- * stores), raises a flag there (release, system scope), waits for the K-vectors of all peers to land in its own mailbox
+ * stores; every 8-byte word carries 32 bits of payload and the launch's 32-bit sequence number, so value and "valid" flag
+ * arrive in one atomic store: no fence, no separate flag), polls its own mailbox until the K-vectors of all peers have landed
  * and adds them in rank order -- so viol_out / loss_out / viol_accum hold the GLOBAL sums, bit-identical on every rank,
  * when the launch completes.  One kernel does the compute and the collective: no NCCL launch, no second kernel.
  *   peers[r]  rank r's exchange buffer (ikl_exchange_bytes() bytes, zero-filled once by its owner before anyone's first

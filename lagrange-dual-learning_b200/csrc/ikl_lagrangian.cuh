@@ -51,14 +51,15 @@ enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
 
 struct alignas(64) TensorMap { unsigned long long opaque[16]; };      // same size and alignment as the driver's CUtensorMap
 
-// One rank's mailbox for the in-kernel exchange of the K sums (include/ikl.h: IklExchange).  mail[parity][r] receives rank
-// r's K-vector of the launch with sequence number seq (parity = seq & 1), flag[parity][r] the sequence number once it has
-// landed.  Two parities suffice: a rank can only be one launch ahead of a peer, because finishing launch s needs every
-// peer's flag of launch s.  `seq` is the owner's private launch counter (device-side, so graph replays advance it).
+// One rank's mailbox for the in-kernel exchange of the K sums (include/ikl.h: IklExchange).  Low-latency protocol: every
+// 8-byte word carries 32 bits of payload and the 32-bit sequence number of the launch that wrote it, so a value and its
+// "valid" flag arrive in ONE store -- no fence, no separate flag, one NVLink latency.  slot[parity][r][i] = the two halves of
+// rank r's double-precision total of constraint i for the launch with sequence number seq (parity = seq & 1).  Two parities
+// suffice: a rank can only be one launch ahead of a peer, because finishing launch s needs every peer's words of launch s.
+// `seq` is the owner's private launch counter (device-side, so graph replays advance it).
 constexpr int kMaxRanks = IKL_MAX_RANKS;
 struct ExchangeBuf {
-  double mail[2][kMaxRanks][kMaxK];
-  unsigned long long flag[2][kMaxRanks];
+  unsigned long long slot[2][kMaxRanks][kMaxK][2];
   unsigned long long seq;
 };
 
@@ -139,53 +140,49 @@ struct SharedAcc {
 };
 
 // ---- in-kernel all-reduce over NVLink peer memory (IklExchange) ---------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
 // Called by the whole LAST block of a rank's launch; thread i < K passes this rank's total of constraint i and gets the
-// global one back.  Push: thread i stores its total into slot [parity][rank][i] of EVERY rank's mailbox (its own included),
-// fences to system scope, the block meets, and thread r < world raises flag[parity][rank] in rank r's mailbox with a
-// release store.  Pull: thread r < world spins (acquire loads) on its own mailbox's flag[parity][r] until rank r's launch
-// with the same sequence number has pushed; the block meets again and thread i adds the K-vectors in rank order -- the same
-// order of the same doubles on every rank, hence bit-identical results.  A peer that never shows up trips the poll limit
-// (seconds) and the kernel traps rather than hanging.
+// global one back.  Push: thread i splits its double into two 32-bit halves, tags each with the launch's sequence number and
+// stores the two 8-byte words into slot [parity][rank][i] of EVERY rank's mailbox (its own included) -- plain NVLink P2P
+// stores, each atomic, so no fence and no flag are needed.  Pull: thread i polls its own mailbox's slot [parity][r][i] for
+// r = 0 .. world-1 until both words carry the sequence number, reassembles the doubles and adds them in rank order -- the
+// same order of the same doubles on every rank, hence bit-identical results.  A peer that never shows up trips the poll
+// limit (seconds) and the kernel traps rather than hanging.
 template <int K>
 __device__ __forceinline__ double exchange_sums(const LagrangianParams& p, double mine) {
   const int tid = threadIdx.x;
   ExchangeBuf* own = p.ex_peer[p.ex_rank];
   const unsigned long long seq = own->seq + 1;      // only this block (the last one) of this rank touches own->seq
   const int par = (int)(seq & 1ull);
-  if (tid < K) {
-    for (int r = 0; r < p.ex_world; ++r) st_relaxed_sys_f64(&p.ex_peer[r]->mail[par][p.ex_rank][tid], mine);
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (tid < p.ex_world) {
-    st_release_sys(&p.ex_peer[tid]->flag[par][p.ex_rank], seq);
-    unsigned long long polls = 0;
-    while (ld_acquire_sys(&own->flag[par][tid]) < seq) {
-      __nanosleep(64);
-      if (++polls > (1ull << 26)) asm volatile("trap;");
-    }
-  }
-  __syncthreads();
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   double tot = 0.0;
   if (tid < K) {
-    for (int r = 0; r < p.ex_world; ++r) tot += ld_relaxed_sys_f64(&own->mail[par][r][tid]);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    for (int r = 0; r < p.ex_world; ++r) {
+      unsigned long long* dst = p.ex_peer[r]->slot[par][p.ex_rank][tid];
+      st_relaxed_sys_u64(dst, w0);
+      st_relaxed_sys_u64(dst + 1, w1);
+    }
+    for (int r = 0; r < p.ex_world; ++r) {
+      const unsigned long long* src = own->slot[par][r][tid];
+      unsigned long long a, b, polls = 0;
+      for (;;) {
+        a = ld_relaxed_sys_u64(src);
+        b = ld_relaxed_sys_u64(src + 1);
+        if ((a & 0xffffffff00000000ull) == tag && (b & 0xffffffff00000000ull) == tag) break;
+        if (++polls > (1ull << 27)) asm volatile("trap;");
+      }
+      tot += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    }
   }
   __syncthreads();
   if (tid == 0) own->seq = seq;

@@ -49,6 +49,24 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   if (!done) mbar_wait_spin(bar, parity);
 }
+// Non-blocking probe of a phase (test_wait never suspends the thread).  The pipelines probe the NEXT tile's "full" barrier
+// right after handing the current stage back, i.e. a whole tile of arithmetic before the answer is needed: the ~90 cycles an
+// mbarrier phase check takes even when the phase is long complete (ncu, profiles/r02/ncu_obs4_stat_planes_final: the branch on
+// its result alone held 6.6 % of all warp-stall samples of the static-obstacle kernel) then overlap the maths instead of
+// standing between two tiles.
+#ifndef IKL_EARLY_PROBE
+#define IKL_EARLY_PROBE 1
+#endif
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
 // Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
 // are zero-filled by the hardware, so ragged last tiles need no special case.
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const TensorMap* tm, int x, int y, unsigned bar) {
@@ -461,8 +479,9 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
 
   int stage = 0;
   unsigned parity = 0;
+  bool ready = false;                                  // the next tile's data was seen complete by an early probe
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar0 + 8 * stage, parity);
+    if (!ready) mbar_wait(bar0 + 8 * stage, parity);
     const long long b = tile * kTmaTile + 2 * tid;
     const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
     f2 th[C::J], ob[C::NOB][3];
@@ -494,6 +513,12 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
       }
     }
     __syncwarp();
+#if IKL_EARLY_PROBE
+    {
+      const int nstage = stage + 1 == S ? 0 : stage + 1;
+      ready = (tile + gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
+    }
+#endif
     if (b < B) body.pair(th, tx, ty, ob, b, b + 1);
     body.tile_done();
     if (++stage == S) {
@@ -622,8 +647,9 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
 
   int stage = 0;
   unsigned parity = 0;
+  bool ready = false;                                  // the next tile's data was seen complete by an early probe
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar0 + 8 * stage, parity);
+    if (!ready) mbar_wait(bar0 + 8 * stage, parity);
     const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
     f2 th[C::J], ob[C::NOB][3];
     const float* tA = reinterpret_cast<const float*>(st) + C::J * tid;
@@ -660,6 +686,12 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
       }
     }
     __syncwarp();
+#if IKL_EARLY_PROBE
+    {
+      const int nstage = stage + 1 == S ? 0 : stage + 1;
+      ready = (tile + gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
+    }
+#endif
     const long long bA = tile * kTmaTile + tid;
     body.pair(th, tx, ty, ob, bA, bA + kThreads);
     body.tile_done();

@@ -133,6 +133,11 @@ class IkLagrangeDualTrainer(object):
     self.model = SimpleNetwork(20, self.opt.num_links, hidden_units=self.opt.hidden_units, depth=8, dropout=0.05).to(self.device)
     ikl_dist.broadcast_parameters(self.model)
     self.use_graph = bool(getattr(self.opt, "cuda_graph", False)) and self.device.type == "cuda"
+    if self.use_graph and self.world > 1 and os.environ.get("IKL_GRAPH_DISTRIBUTED", "0") != "1":
+      # Capturing the flat NCCL all-reduce of the gradients inside the step graph is implemented (ikl/graph_step.py) but hung
+      # on the two-GPU box of this pool (tests/test_gpu_multi.py, round 2): off unless IKL_GRAPH_DISTRIBUTED=1.
+      print("NOTE: --cuda_graph under torch.distributed is experimental (set IKL_GRAPH_DISTRIBUTED=1); running eagerly")
+      self.use_graph = False
     if self.use_graph and self.opt.batch_size % self.world != 0:
       print("NOTE: --cuda_graph needs --batch_size divisible by the world size (every rank replays the same graph); running eagerly")
       self.use_graph = False
