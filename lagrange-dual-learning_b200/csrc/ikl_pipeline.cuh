@@ -49,13 +49,14 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   if (!done) mbar_wait_spin(bar, parity);
 }
-// Non-blocking probe of a phase (test_wait never suspends the thread).  The pipelines probe the NEXT tile's "full" barrier
-// right after handing the current stage back, i.e. a whole tile of arithmetic before the answer is needed: the ~90 cycles an
-// mbarrier phase check takes even when the phase is long complete (ncu, profiles/r02/ncu_obs4_stat_planes_final: the branch on
-// its result alone held 6.6 % of all warp-stall samples of the static-obstacle kernel) then overlap the maths instead of
-// standing between two tiles.
+// Non-blocking probe of a phase (test_wait never suspends the thread).  IKL_EARLY_PROBE=1 probes the NEXT tile's "full"
+// barrier right after handing the current stage back, a whole tile of arithmetic before the answer is needed, to take the
+// ~90-cycle phase check off the path between two tiles (the branch on its result held 6.6 % of the warp-stall samples of the
+// static-obstacle kernel, profiles/r02/ncu_obs4_stat_planes_final).  Measured (profiles/r02/kernel_table_probe.jsonl, interleaved
+// A/B): 1-5 % SLOWER on the static / unconstrained configs, +-0.5 % on the dynamic one -- the probe mostly comes back "not
+// yet" (the refill is issued by the block's slowest warp) and the blocking wait follows anyway.  Rejected; off by default.
 #ifndef IKL_EARLY_PROBE
-#define IKL_EARLY_PROBE 1
+#define IKL_EARLY_PROBE 0
 #endif
 __device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
   unsigned done;
