@@ -422,8 +422,12 @@ def strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms
   res.update({"ms_per_step": step_ms, "samples_per_s": total / (step_ms * 1e-3), "exchange_overhead_us": (step_ms - local_ms) * 1e3,
               "ideal_ms": ideal, "efficiency_vs_ideal": ideal / step_ms,
               "frac_of_hbm_peak": ALGO_BYTES_PER_SAMPLE * Bs / (step_ms * 1e-3) / 1e9 / measured_peak()[0],
-              "limiter": "fixed per-launch cost (grid ramp-up, tail, final reduction: kernel_only_ms vs ideal_ms) "
-                         "and the in-kernel exchange (exchange_overhead_us); no host or NCCL launch in the loop"})
+              "fixed_launch_cost_us": (local_ms - ideal) * 1e3})
+  fixed_us, ex_us = res["fixed_launch_cost_us"], res["exchange_overhead_us"]
+  res["limiter"] = ("%s: the part of a launch that does not shrink with the shard -- graph-node launch gap, pipeline ramp-up, tail and the "
+                    "final reduction -- costs %.1f us per step, the in-step exchange %.1f us, against %.1f us of streaming at the HBM rate; "
+                    "no host and no NCCL launch is in the loop" % (
+                        "fixed per-launch cost" if fixed_us >= ex_us else "exchange latency + rank skew", fixed_us, ex_us, ideal * 1e3))
   return res
 
 
