@@ -73,7 +73,10 @@ class GraphedTrainStep(object):
         self._one_step()
       self.graph = torch.cuda.CUDAGraph()
       self.optimizer.zero_grad(set_to_none=True)
-      with torch.cuda.graph(self.graph, stream=side):
+      # under torch.distributed NCCL's watchdog thread polls CUDA events while this thread captures: only this thread's
+      # calls may be policed by the capture
+      mode = "thread_local" if ikl_dist.is_distributed() else "global"
+      with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):
         self.viol, self.loss = self._one_step()
     torch.cuda.current_stream(self.x.device).wait_stream(side)
     self.model.load_state_dict(weights)
