@@ -156,10 +156,15 @@ IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const I
                                                     float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
                                                     const IklExchange* ex, void* stream);
 
-/* Backward alone: d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights w (for autograd:
+/* Gradient alone: d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights w (for autograd:
  * w_i = grad(lagrange_loss) * lambda_i + grad(constraint_violations)_i).  Recomputes from the inputs -- nothing is
  * saved by the forward pass -- and replaces the autograd tape between lagrange_loss and the network output
- * (scripts/trainer.py:264).  Same kernel as ikl_lagrangian_forward_backward; the sums it produces are discarded. */
+ * (scripts/trainer.py:264).  This is also the launch of a TRAINING step: train_with_relaxation consumes nothing of
+ * process_batch's outputs but lagrange_loss.backward() (scripts/trainer.py:262-265), so no constraint sum is needed there.
+ * On the staged layouts (rows >= 512, TMA planes) it runs the GRADIENT-ONLY specialisations of the fused kernels: same
+ * per-sample arithmetic as ikl_lagrangian_forward_backward (dtheta is bit-identical), but no running sums, no reduction,
+ * no partials, nothing written but dtheta.  Other layouts run the full kernel and discard its sums (IKL_BACKWARD_SUMS=1
+ * forces that everywhere). */
 IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
                                   float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj, void* stream);
 

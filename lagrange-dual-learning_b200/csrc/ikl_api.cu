@@ -122,6 +122,10 @@ void fill_packed_uniforms(const IklSpec* spec, const Uniforms& u, PackedUniforms
     for (int c = 0; c < 3; ++c) pu.stat_ob[o][c] = dup(u.stat_ob[o][c]);
   for (int o = 0; o < kMaxObst; ++o) pu.stat_thr[o] = dup(u.stat_ob[o][2] * kNearTie);      // fl(r * 2^-20): exact scaling
   for (int i = 0; i < kMaxK; ++i) pu.lam[i] = dup(u.w[i]);
+  for (int i = 0; i < kMaxK; ++i) {
+    pu.ob_nlo_lam[i] = dup(pu.ob_nlo.x * u.w[i]);          // fp32 products, the roundings the kernels' own FMUL2 would make
+    pu.ob_nhi_lam[i] = dup(pu.ob_nhi_sel.x * u.w[i]);
+  }
   for (int m = 0; m < kMaxLinks; ++m) pu.link[m] = dup(u.link[m]);
 }
 
@@ -263,7 +267,7 @@ namespace {
 
 IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
               double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
-              void* stream, const IklExchange* ex = nullptr) {
+              void* stream, const IklExchange* ex = nullptr, bool sums = true) {
   IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
   if (st != IKL_OK) return st;
   if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
@@ -277,7 +281,7 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
   Variant v;
   const int layout = prepare_lagrangian_params(spec, in, w->host, grad, dtheta, dt_sb, dt_sj, p, v);
   if (layout < 0) return (IklStatus)(-layout);
-  v.mode = !grad ? kFwd : (w->host ? kGradHostW : kGradDevW);
+  v.mode = !grad ? kFwd : (sums ? (w->host ? kGradHostW : kGradDevW) : (w->host ? kGradOnlyHostW : kGradOnlyDevW));
   p.q_ee = q_ee_out;
   p.err_sq = err_sq_out;
   p.w_dev = w->device;
@@ -361,9 +365,12 @@ IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const I
 IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* dtheta,
                                   int64_t dtheta_sb, int64_t dtheta_sj, void* stream) {
   if (!workspace) return IKL_ERR_INVALID_ARGUMENT;
-  // the sums are a by-product of the pass; they land in the scratch tail of the workspace (after the completion counter)
+  // gradient-only kernels where they exist (the staged layouts): no sums are formed at all.  Elsewhere the sums are a
+  // by-product of the pass and land in the scratch tail of the workspace (after the completion counter).
   float* scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kPartialsBytes + 64);
-  return run(spec, in, w, workspace, scratch, scratch + kMaxK, nullptr, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream);
+  static const bool with_sums = [] { const char* e = getenv("IKL_BACKWARD_SUMS"); return e && e[0] == '1'; }();
+  return run(spec, in, w, workspace, scratch, scratch + kMaxK, nullptr, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream,
+             nullptr, with_sums);
 }
 
 int32_t ikl_abi_version(void) { return IKL_ABI_VERSION; }

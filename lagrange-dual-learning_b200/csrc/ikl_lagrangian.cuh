@@ -47,7 +47,9 @@ constexpr int kFinalParts = kThreads / kMaxK;   // 16 partial chains in the last
 #endif
 
 enum Layout : int { kStrided = 0, kRows = 1, kPlanes = 2 };
-enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2 };
+// kGradOnly*: d/dtheta alone -- no running sums, no reduction, no viol_out / loss_out (staged kernels only; other kernels
+// serve such a request with the corresponding kGrad* mode and discard the sums)
+enum Mode : int { kFwd = 0, kGradHostW = 1, kGradDevW = 2, kGradOnlyHostW = 3, kGradOnlyDevW = 4 };
 
 struct alignas(64) TensorMap { unsigned long long opaque[16]; };      // same size and alignment as the driver's CUtensorMap
 
@@ -98,6 +100,9 @@ template <int LAYOUT_, int J_, int NOBS_, bool DYN_, bool JL_, int MODE_, bool U
 struct Cfg {
   static constexpr int LAYOUT = LAYOUT_, J = J_, NOBS = NOBS_, MODE = MODE_;
   static constexpr bool DYN = DYN_, JL = JL_, UNIT = UNIT_, GRAD = MODE_ != kFwd;
+  static constexpr bool SUMS = MODE_ != kGradOnlyHostW && MODE_ != kGradOnlyDevW;      // the K running sums are formed
+  static constexpr bool DEVW = MODE_ == kGradDevW || MODE_ == kGradOnlyDevW;           // multipliers read from device memory
+  using WithSums = Cfg<LAYOUT_, J_, NOBS_, DYN_, JL_, MODE_ == kGradOnlyHostW ? kGradHostW : (MODE_ == kGradOnlyDevW ? kGradDevW : MODE_), UNIT_>;
   static constexpr int K = num_constraints(J_, NOBS_, JL_);
   static constexpr int NOB = NOBS_ > 0 ? NOBS_ : 1;
 };
@@ -506,7 +511,7 @@ __device__ __forceinline__ void run_planes_packed(const LagrangianParams& p, con
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
 #pragma unroll
       for (int j = 0; j < C::J; ++j) stg_stream_f2(p.dtheta + j * p.dt_sj + b, dth[j]);
@@ -556,7 +561,7 @@ __device__ __forceinline__ void run_rows_packed(const LagrangianParams& p, const
     } else {
       static_obstacles_packed<C>(p, ob);
     }
-    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, true, C::DYN, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     if (C::GRAD) {
       float* dA = p.dtheta + bA * C::J;
       float* dB = p.dtheta + bB * C::J;
@@ -664,6 +669,10 @@ cudaError_t resident_blocks(Kernel kernel, size_t smem, int (&cache)[64], int* o
 
 template <class C>
 cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_blocks, const char* name) {
+  if constexpr (!C::SUMS) {
+    // gradient-only specialisations exist for the staged kernels; everything else runs the full kernel (sums discarded)
+    if (!p.use_tma || C::LAYOUT == kStrided) return launch_cfg<typename C::WithSums>(p, stream, max_blocks, name);
+  }
   if constexpr (C::LAYOUT == kPlanes) {
     if (p.use_tma) {
       static int cache[64] = {0};
@@ -700,22 +709,26 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       return cudaGetLastError();
     }
   }
-  static int cache[64] = {0};
-  int blocks_per_sm = 1;
-  {
-    const cudaError_t e = resident_blocks(lagrangian_kernel<C>, 0, cache, &blocks_per_sm);
-    if (e != cudaSuccess) return e;
+  if constexpr (C::SUMS) {
+    static int cache[64] = {0};
+    int blocks_per_sm = 1;
+    {
+      const cudaError_t e = resident_blocks(lagrangian_kernel<C>, 0, cache, &blocks_per_sm);
+      if (e != cudaSuccess) return e;
+    }
+    const long long per_block = (long long)kThreads * (C::LAYOUT == kStrided ? IKL_ROWS_UNROLL : 2);
+    long long tiles = (p.batch + per_block - 1) / per_block;
+    if (tiles < 1) tiles = 1;
+    long long grid = (long long)grid_sms() * blocks_per_sm;
+    if (grid > tiles) grid = tiles;
+    if (grid > max_blocks) grid = max_blocks;
+    set_last_kernel_name(name);
+    count_launch();
+    lagrangian_kernel<C><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;      // unreachable: handled by the redirection at the top
   }
-  const long long per_block = (long long)kThreads * (C::LAYOUT == kStrided ? IKL_ROWS_UNROLL : 2);
-  long long tiles = (p.batch + per_block - 1) / per_block;
-  if (tiles < 1) tiles = 1;
-  long long grid = (long long)grid_sms() * blocks_per_sm;
-  if (grid > tiles) grid = tiles;
-  if (grid > max_blocks) grid = max_blocks;
-  set_last_kernel_name(name);
-  count_launch();
-  lagrangian_kernel<C><<<(unsigned)grid, kThreads, 0, stream>>>(p);
-  return cudaGetLastError();
 }
 
 // Key of a specialisation inside one (LAYOUT, J, UNIT) family.

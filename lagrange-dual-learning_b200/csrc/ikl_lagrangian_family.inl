@@ -17,13 +17,23 @@ cudaError_t launch_mode(const Variant& v, const LagrangianParams& p, cudaStream_
   static const char* const layout_names[] = {"strided", "rows", "planes"};
   const bool rows_tma = L == kRows && p.use_tma && RowsTmaLayout<Cfg<L, J, NOBS, DYN, JL, kFwd, UNIT>>::kSupported;
   const char* lname = (L == kPlanes && p.use_tma) ? "planes_tma" : (rows_tma ? "rows_tma" : layout_names[L]);
-  static const char* const mode_names[] = {"fwd", "fwdbwd_hostw", "fwdbwd_devw"};
+  static const char* const mode_names[] = {"fwd", "fwdbwd_hostw", "fwdbwd_devw", "grad_hostw", "grad_devw"};
+  const bool grad_only = v.mode == kGradOnlyHostW || v.mode == kGradOnlyDevW;
+  // gradient-only specialisations exist for the staged kernels only (launch_cfg redirects the rest to the full kernel)
+  const bool staged = p.use_tma && (L == kPlanes || rows_tma);
+  const int shown = (grad_only && !staged) ? (v.mode == kGradOnlyHostW ? kGradHostW : kGradDevW) : v.mode;
   snprintf(name, sizeof(name), "ikl_lagrangian<%s,J%d,obs%d,%s,%s,%s,%s>", lname, J, NOBS, DYN ? "dyn" : "stat",
-           JL ? "jl" : "nojl", mode_names[v.mode], UNIT ? "unit" : "len");
+           JL ? "jl" : "nojl", mode_names[shown], UNIT ? "unit" : "len");
   switch (v.mode) {
     case kFwd: return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kFwd, UNIT>>(p, stream, max_blocks, name);
     case kGradHostW: return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradHostW, UNIT>>(p, stream, max_blocks, name);
     case kGradDevW: return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradDevW, UNIT>>(p, stream, max_blocks, name);
+    case kGradOnlyHostW:
+      if constexpr (L == kStrided) return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradHostW, UNIT>>(p, stream, max_blocks, name);
+      else return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradOnlyHostW, UNIT>>(p, stream, max_blocks, name);
+    case kGradOnlyDevW:
+      if constexpr (L == kStrided) return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradDevW, UNIT>>(p, stream, max_blocks, name);
+      else return launch_cfg<Cfg<L, J, NOBS, DYN, JL, kGradOnlyDevW, UNIT>>(p, stream, max_blocks, name);
   }
   return cudaErrorInvalidValue;
 }

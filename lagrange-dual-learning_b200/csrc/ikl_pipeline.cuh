@@ -120,7 +120,7 @@ static __device__ __noinline__ void redo_pair_exact(const LagrangianParams& p, c
   }
 #pragma unroll
   for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
-  eval_pair<C::J, C::UNIT, C::NOBS, C::JL, true, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+  eval_pair<C::J, C::UNIT, C::NOBS, C::JL, true, true, C::DYN, false>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
 #pragma unroll
   for (int j = 0; j < C::J; ++j) {
     p.dtheta[bA * p.dt_sb + j * p.dt_sj] = f2_lo(dth[j]);
@@ -158,7 +158,7 @@ struct LagrangianBody {
   }
   __device__ __forceinline__ void pair(const f2 (&th)[C::J], f2 tx, f2 ty, const f2 (&ob)[C::NOB][3], long long bA, long long bB) {
     f2 dth[C::J], ee[3];
-    const bool near_tie = eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, kExact, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, ndiff);
+    const bool near_tie = eval_pair<C::J, C::UNIT, C::NOBS, C::JL, C::GRAD, kExact, C::DYN, C::SUMS>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, ndiff);
     if (C::GRAD) {
       if (C::LAYOUT == kPlanes) {                       // bB == bA + 1: one 8-byte store per plane
 #pragma unroll
@@ -180,13 +180,16 @@ struct LagrangianBody {
     }
   }
   __device__ __forceinline__ void flush() {
-    if constexpr (kPermuted) sacc.template flush_xor4<kObstBase, C::J>(acc, r);
+    if constexpr (!C::SUMS) return;             // gradient-only: there are no sums
+    else if constexpr (kPermuted) sacc.template flush_xor4<kObstBase, C::J>(acc, r);
     else sacc.flush(acc);
   }
   __device__ __forceinline__ void tile_done() {
-    if (++since_flush == kFlushSamples / 2) {
-      since_flush = 0;
-      flush();
+    if constexpr (C::SUMS) {
+      if (++since_flush == kFlushSamples / 2) {
+        since_flush = 0;
+        flush();
+      }
     }
   }
   __device__ __forceinline__ void finish() { flush(); }
@@ -225,7 +228,7 @@ __device__ __forceinline__ void stage_pair_weights(const float* w_dev, float2* l
 }
 
 template <class C>
-constexpr bool use_single_static() { return IKL_STATIC_SINGLE && !IKL_EXACT_GRAD && !C::DYN && C::NOBS > 0 && C::J == 3 && C::UNIT; }
+constexpr bool use_single_static() { return IKL_STATIC_SINGLE && !IKL_EXACT_GRAD && C::SUMS && !C::DYN && C::NOBS > 0 && C::J == 3 && C::UNIT; }
 
 template <class C, class W1, class W2>
 struct SingleStaticBody {
@@ -355,7 +358,7 @@ struct StatsBody {
 #pragma unroll
     for (int i = 0; i < C::K; ++i) acc[i] = f2_splat(0.f);
     const PackedHostWeights w2{p.pu};
-    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, false, true, C::DYN>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
+    eval_pair<C::J, C::UNIT, C::NOBS, C::JL, false, true, C::DYN, true>(p.pu, w2, th, tx, ty, ob, acc, dth, ee, as_f2(p.pu.ob_ndiff));
     float v[C::K];
 #pragma unroll
     for (int i = 0; i < C::K; ++i) v[i] = f2_lo(acc[i]);
@@ -536,8 +539,20 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
 #ifndef IKL_STATIC_MIN_BLOCKS
 #define IKL_STATIC_MIN_BLOCKS 2
 #endif
+// The gradient-only kernels carry no running sums (up to 32 registers less).  Measured (profiles/r02/kernel_table_gradonly.jsonl,
+// same-run A/B at 2^24 samples): with ONE static obstacle they fit a third resident block without spills (78-80 registers) and
+// gain 3-9 % from it (planes 0.108 -> 0.098-0.101 ms, rows 0.107 -> 0.103 ms); with four static obstacles the third block
+// costs 64-72 bytes of spills and 5 % of the time, and the kernels WITH sums lose up to 35 % (600 bytes of spills).
+#ifndef IKL_GRADONLY_STATIC_MIN_BLOCKS
+#define IKL_GRADONLY_STATIC_MIN_BLOCKS 0          // 0: three blocks for one static obstacle, IKL_STATIC_MIN_BLOCKS otherwise
+#endif
 template <class C>
-constexpr int staged_min_blocks() { return C::DYN ? IKL_MIN_BLOCKS : IKL_STATIC_MIN_BLOCKS; }
+constexpr int staged_min_blocks() {
+  if (C::DYN) return IKL_MIN_BLOCKS;
+  if (C::SUMS) return IKL_STATIC_MIN_BLOCKS;
+  if (IKL_GRADONLY_STATIC_MIN_BLOCKS > 0) return IKL_GRADONLY_STATIC_MIN_BLOCKS;
+  return C::NOBS == 1 ? 3 : IKL_STATIC_MIN_BLOCKS;
+}
 
 template <class C>
 __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_planes_tma_kernel(const __grid_constant__ LagrangianParams p) {
@@ -548,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_p
   __shared__ double s_warp[kWarps][kMaxK];
   __shared__ float s_lam1[kMaxK];
   __shared__ float2 s_lam_pairs[3][kMaxObstPairs];
-  if constexpr (C::MODE == kGradDevW) {
+  if constexpr (C::DEVW) {
     if (threadIdx.x < C::K) {
       const float l = __ldg(p.w_dev + threadIdx.x);
       s_lam2[threadIdx.x] = make_float2(l, l);
@@ -566,16 +581,16 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_p
         SingleStaticBody<C, std::decay_t<decltype(w1)>, std::decay_t<decltype(w2)>> body(p, w1, w2, sacc, &s_ndiff);
         run_planes_pipe<C>(p, body, dyn_smem, bars);
       };
-      if constexpr (C::MODE == kGradDevW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
+      if constexpr (C::DEVW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
       else run1(SingleHostWeights{p});
     } else {
       LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2, sacc, 0, &s_ndiff);
       run_planes_pipe<C>(p, body, dyn_smem, bars);
     }
   };
-  if constexpr (C::MODE == kGradDevW) run(PackedSmemWeights{s_lam2});
+  if constexpr (C::DEVW) run(PackedSmemWeights{s_lam2});
   else run(PackedHostWeights{p.pu});
-  block_finalize<C::K>(p, s_warp);
+  if constexpr (C::SUMS) block_finalize<C::K>(p, s_warp);
 }
 
 // ---- rows layout, bulk-copy staged -------------------------------------------------------------------------------------
@@ -712,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_r
   __shared__ float2 s_lam_perm[4][kMaxK];      // multipliers as (w, w) pairs, obstacle entries permuted by k ^ r
   __shared__ double s_warp[kWarps][kMaxK];
   const int r = L::kPermuted ? ((threadIdx.x >> 1) & 3) : 0;
-  constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::MODE == kGradDevW);
+  constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::DEVW);
   if constexpr (kSmemWeights) {
     if (threadIdx.x < 4 * kMaxK) {
       const int rr = threadIdx.x / kMaxK, i = threadIdx.x % kMaxK;
@@ -722,13 +737,13 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_r
         src = L::kObstBase + C::J * (k ^ rr) + j;
       }
       float l = 0.f;
-      if (i < C::K) l = (C::MODE == kGradDevW) ? __ldg(p.w_dev + src) : p.u.w[src];
+      if (i < C::K) l = (C::DEVW) ? __ldg(p.w_dev + src) : p.u.w[src];
       s_lam_perm[rr][i] = make_float2(l, l);
     }
   }
   __shared__ float s_lam1[kMaxK];
   __shared__ float2 s_lam_pairs[3][kMaxObstPairs];
-  if constexpr (C::MODE == kGradDevW && use_single_static<C>()) {
+  if constexpr (C::DEVW && use_single_static<C>()) {
     if (threadIdx.x < C::K) s_lam1[threadIdx.x] = __ldg(p.w_dev + threadIdx.x);
     stage_pair_weights<C>(p.w_dev, &s_lam_pairs[0][0]);
   }
@@ -742,7 +757,7 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_r
         SingleStaticBody<C, std::decay_t<decltype(w1)>, std::decay_t<decltype(w2_plain)>> body(p, w1, w2_plain, sacc, &s_ndiff);
         run_rows_pipe<C>(p, body, dyn_smem, bars, r);
       };
-      if constexpr (C::MODE == kGradDevW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
+      if constexpr (C::DEVW) run1(SingleSmemWeights{s_lam1, &s_lam_pairs[0][0]});
       else run1(SingleHostWeights{p});
     } else {
       LagrangianBody<C, std::decay_t<decltype(w2)>> body(p, w2, w2_plain, sacc, r, &s_ndiff);
@@ -767,12 +782,12 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_r
       }
     };
     if (full < p.batch) {
-      if constexpr (C::MODE == kGradDevW) tail(DeviceWeights<C::K>(p.u, p.w_dev));
+      if constexpr (C::DEVW) tail(DeviceWeights<C::K>(p.u, p.w_dev));
       else tail(HostWeights(p.u, nullptr));
     }
-    sacc.flush(sacc1);
+    if constexpr (C::SUMS) sacc.flush(sacc1);
   }
-  block_finalize<C::K>(p, s_warp);
+  if constexpr (C::SUMS) block_finalize<C::K>(p, s_warp);
 }
 
 // ---- evaluation statistics through the same pipelines -------------------------------------------------------------------

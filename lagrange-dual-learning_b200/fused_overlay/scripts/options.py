@@ -49,6 +49,10 @@ class Options(object):
                              help="Batch size of the validation loader (dual step and validation pass); 0 = --batch_size as in "
                                   "the reference.  The sums are additive, so a few large batches give the same dual step "
                                   "(up to the dropout draws of the reference's train-mode validation) in far fewer launches")
+    self.parser.add_argument("--train_sums", action="store_true", default=False,
+                             help="Also form the constraint sums and the Lagrangian's value in every TRAINING step.  The reference's "
+                                  "training loop consumes only lagrange_loss.backward() (trainer.py:262-265), so by default those "
+                                  "launches are the gradient-only kernel; dual steps and validation always compute the sums")
     self.parser.add_argument("--load_multipliers", action="store_true", default=False,
                              help="Also reload multipliers.pth from --load_weights_folder (the reference restarts lambda)")
 

@@ -142,6 +142,7 @@ class IkLagrangeDualTrainer(object):
       print("NOTE: --cuda_graph needs --batch_size divisible by the world size (every rank replays the same graph); running eagerly")
       self.use_graph = False
     self._unit_upstream = False
+    self._grad_only = False                    # inside train_with_relaxation: gradient-only launches (unless --train_sums)
     self.optimizer = Adam(self.model.parameters(), lr=self.opt.optimizer_lr, betas=(0.9, 0.999), capturable=self.use_graph)
     self._graph_step = None
 
@@ -255,7 +256,7 @@ class IkLagrangeDualTrainer(object):
     outputs = BatchOutputs({"q_ee_actual": side_outputs, "position_err_sq": side_outputs, "joint_angle_l2": angle_l2})
     outputs["pred_joint_theta"] = pred_joint_theta
     viol, loss = fused.FusedIkLagrangian.apply(pred_joint_theta, q_ee_desired, obstacles, lamda, spec,
-                                               self._host_multipliers(lamda), self._unit_upstream)
+                                               self._host_multipliers(lamda), self._unit_upstream, self._grad_only)
     outputs["constraint_violations"] = viol
     outputs["lagrange_loss"] = loss
     return outputs
@@ -309,7 +310,8 @@ class IkLagrangeDualTrainer(object):
     if self.use_graph and self._graph_step is None:
       from ikl.graph_step import GraphedTrainStep
       self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size // self.world, self.device,
-                                          planes=bool(getattr(self.opt, "device_data", False)))
+                                          planes=bool(getattr(self.opt, "device_data", False)),
+                                          grad_only=not getattr(self.opt, "train_sums", False))
     if self._graph_step is not None:
       self._graph_step.set_multipliers(lamda)
     for ti, inputs in enumerate(self.train_loader):
@@ -320,10 +322,14 @@ class IkLagrangeDualTrainer(object):
         self._graph_step.step(inputs)          # the whole step (forward, Lagrangian, backward, all-reduce, Adam) is one graph replay
         continue
       self._unit_upstream = True               # .backward() below starts at the Lagrangian itself: no gradient rescaling pass
+      # ... and nothing else of `outputs` is consumed here (trainer.py:262-265): the launch is the gradient-only kernel,
+      # constraint_violations / lagrange_loss are NaN placeholders carrying the autograd edge (--train_sums: the full kernel)
+      self._grad_only = not getattr(self.opt, "train_sums", False) and not getattr(self.opt, "unfused", False)
       try:
         outputs = self.process_batch(inputs, lamda)
       finally:
         self._unit_upstream = False
+        self._grad_only = False
       self.model.zero_grad()
       outputs["lagrange_loss"].backward()
       ikl_dist.all_reduce_gradients(self.model)

@@ -179,7 +179,9 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
 
 
 def lagrangian_backward(spec, theta, q_ee_desired, obstacles, weights, dtheta=None):
-  """d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights (host list or CUDA tensor): the backward pass alone."""
+  """d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights (host list or CUDA tensor): the backward pass alone.
+  On the staged layouts this is the gradient-only kernel (no running sums, no reduction); its d/dtheta equals
+  lagrangian_forward_backward's bit for bit."""
   lib = _cabi.load()
   K = spec.num_constraints
   desc, keep = _batch_desc(spec, theta, q_ee_desired, obstacles)
@@ -233,6 +235,10 @@ class FusedIkLagrangian(torch.autograd.Function):
   unit_upstream=True is the caller's promise that backward() starts at lagrange_loss itself with gradient 1 (what
   scripts/trainer.py:264 does); the scaling pass `dtheta * grad_loss` is then skipped.
 
+  grad_only=True (needs unit_upstream) is for a training step, which consumes nothing but lagrange_loss.backward()
+  (scripts/trainer.py:262-265): the launch is the GRADIENT-ONLY kernel -- d(loss)/d(theta), no running sums, no reduction --
+  and the two returned tensors are NaN placeholders that only carry the autograd edge.
+
   Differentiable w.r.t. theta only (targets, obstacles, limits and lam carry no gradient in the reference).
   When theta needs a gradient the forward launch already produces d(sum_i lam_i g_i)/d(theta); backward
   scales it by the incoming gradient of lagrange_loss.  A non-trivial gradient flowing into
@@ -240,12 +246,20 @@ class FusedIkLagrangian(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False):
+  def forward(ctx, theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False, grad_only=False):
     ctx.set_materialize_grads(False)
     ctx.spec = spec
     ctx.unit_upstream = bool(unit_upstream)
+    ctx.grad_only = bool(grad_only) and ctx.needs_input_grad[0]
+    if grad_only and not unit_upstream:
+      raise ValueError("grad_only=True needs unit_upstream=True: without the sums only d(lagrange_loss)/d(theta) itself is available")
     weights = lam_host if lam_host is not None else lam
-    if ctx.needs_input_grad[0]:
+    if ctx.grad_only:
+      dtheta = lagrangian_backward(spec, theta.detach(), q_ee_desired, obstacles if spec.dynamic else None, weights)
+      nan = torch.full((spec.num_constraints + 1,), float("nan"), dtype=torch.float32, device=theta.device)
+      viol, loss = nan[:-1], nan[-1]
+      ctx.save_for_backward(theta, q_ee_desired, obstacles if spec.dynamic else None, lam, dtheta)
+    elif ctx.needs_input_grad[0]:
       viol, loss, dtheta = lagrangian_forward_backward(spec, theta.detach(), q_ee_desired, obstacles, weights)
       ctx.save_for_backward(theta, q_ee_desired, obstacles if spec.dynamic else None, lam, dtheta)
     else:
@@ -256,24 +270,32 @@ class FusedIkLagrangian(torch.autograd.Function):
   @staticmethod
   def backward(ctx, grad_viol, grad_loss):
     theta, q_ee_desired, obstacles, lam, dtheta = ctx.saved_tensors
+    if ctx.grad_only:
+      if grad_viol is not None:
+        raise RuntimeError("grad_only=True: the constraint sums were not computed and cannot be differentiated")
+      if grad_loss is None:
+        return (None,) * 8
+      if _CHECK_UNIT_UPSTREAM:
+        assert float(grad_loss) == 1.0, "grad_only=True but lagrange_loss received gradient %r" % float(grad_loss)
+      return (dtheta,) + (None,) * 7
     if grad_viol is None:
       if grad_loss is None:
-        return (None,) * 7
+        return (None,) * 8
       if ctx.unit_upstream:
         # the caller differentiates lagrange_loss itself (scripts/trainer.py:264: outputs["lagrange_loss"].backward()), so
         # the incoming gradient is 1 and the kernel's d(loss)/d(theta) is returned as written: no extra pass over (B,J)
         if _CHECK_UNIT_UPSTREAM:
           assert float(grad_loss) == 1.0, "unit_upstream=True but lagrange_loss received gradient %r" % float(grad_loss)
-        return dtheta, None, None, None, None, None, None
-      return dtheta * grad_loss, None, None, None, None, None, None
+        return (dtheta,) + (None,) * 7
+      return (dtheta * grad_loss,) + (None,) * 7
     lam_dev = lam if (isinstance(lam, torch.Tensor) and lam.is_cuda) else torch.as_tensor(lam, dtype=torch.float32, device=theta.device)
     w = grad_viol if grad_loss is None else grad_viol + grad_loss * lam_dev
     g = lagrangian_backward(ctx.spec, theta.detach(), q_ee_desired, obstacles, w.contiguous())
-    return g, None, None, None, None, None, None
+    return (g,) + (None,) * 7
 
 
-def ik_lagrangian(theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False):
+def ik_lagrangian(theta, q_ee_desired, obstacles, lam, spec, lam_host=None, unit_upstream=False, grad_only=False):
   """Functional form of FusedIkLagrangian: returns (constraint_violations, lagrange_loss)."""
   if not isinstance(lam, torch.Tensor):
     lam = torch.as_tensor(lam, dtype=torch.float32)
-  return FusedIkLagrangian.apply(theta, q_ee_desired, obstacles, lam, spec, lam_host, unit_upstream)
+  return FusedIkLagrangian.apply(theta, q_ee_desired, obstacles, lam, spec, lam_host, unit_upstream, grad_only)

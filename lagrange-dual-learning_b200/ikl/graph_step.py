@@ -7,6 +7,8 @@ once and replaying it removes the Python and launch overhead at any batch size; 
 C ABI on the capturing stream like any other kernel.  The multipliers are read from a device tensor inside the graph
 (IklWeights.device), so a dual-ascent update needs no re-capture: copy the new lambda into `self.lam`.
 
+  grad_only=True    the Lagrangian launch is the gradient-only kernel (a training step consumes nothing but
+                    lagrange_loss.backward(), scripts/trainer.py:262-265); step() then returns NaN placeholders.
   planes=True       the static input buffers are structure-of-arrays planes and the network's last layer is evaluated
                     transposed (SimpleNetwork.forward_planes), so the TMA-staged planes kernel is the one in the graph --
                     what `--device_data` batches arrive as.
@@ -20,7 +22,7 @@ from . import fused
 
 
 class GraphedTrainStep(object):
-  def __init__(self, model, optimizer, spec, batch_size, device, warmup=3, planes=False):
+  def __init__(self, model, optimizer, spec, batch_size, device, warmup=3, planes=False, grad_only=False):
     if not torch.cuda.is_available():
       raise RuntimeError("CUDA graphs need a CUDA device")
     for group in optimizer.param_groups:
@@ -28,6 +30,7 @@ class GraphedTrainStep(object):
         raise ValueError("construct the optimizer with capturable=True (its step counter must live on the device)")
     self.model, self.optimizer, self.spec = model, optimizer, spec
     self.planes = bool(planes)
+    self.grad_only = bool(grad_only)      # the step's launch is the gradient-only kernel; self.viol / self.loss are NaN placeholders
     dev = torch.device(device)
     B, K = int(batch_size), spec.num_constraints        # B: THIS rank's share of the batch
     self.batch_size = B
@@ -48,7 +51,7 @@ class GraphedTrainStep(object):
     theta = self.model.forward_planes(self.x) if self.planes else self.model(self.x)
     # unit_upstream: loss.backward() is called on the Lagrangian itself (scripts/trainer.py:264), so d(loss)/d(theta) is
     # the kernel's output as written -- no rescaling pass
-    viol, loss = fused.FusedIkLagrangian.apply(theta, self.q_des, self.obst, self.lam, self.spec, None, True)
+    viol, loss = fused.FusedIkLagrangian.apply(theta, self.q_des, self.obst, self.lam, self.spec, None, True, self.grad_only)
     self.optimizer.zero_grad(set_to_none=True)
     loss.backward()
     ikl_dist.all_reduce_gradients(self.model)

@@ -718,6 +718,54 @@ def test_ties_through_the_staged_kernels(cuda_device, monkeypatch):
   close(d_x[special].cpu()[ok].numpy(), ref[ok].numpy(), scale=float(ref[ok].abs().max()), rtol=2e-6)
 
 
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_gradient_only_kernels_match_the_full_kernels(name, cuda_device, monkeypatch):
+  """ikl_lagrangian_backward runs the gradient-only specialisations of the staged kernels (no running sums, no reduction:
+  what a training step needs, scripts/trainer.py:262-265 consumes only lagrange_loss.backward()).  Their d/dtheta must equal
+  the full kernels' bit for bit -- same arithmetic minus the sums -- in both staged layouts, with host and device
+  multipliers, on whole tiles, ragged tails and tie samples; a sums launch right after must find the workspace intact."""
+  from ikl import fused, synthetic, _cabi
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  spec, ospec = specs_for(name)
+  dev = cuda_device
+  K = spec.num_constraints
+  lam = (0.5 + 0.1 * np.arange(K)).astype(np.float32)
+  lim = float(np.float32(2.094395))
+  for B in (512, 2048 + 516, 1 << 16):
+    theta, q_des, obst = synthetic.make_batch(B, seed=B)
+    for n, b in enumerate(range(3, B, 211)):           # ties and near ties: joints on a limit, a tip on a (dynamic) circle
+      if n % 2 == 0:
+        theta[b] = torch.tensor([lim, -lim, 0.0])
+      else:
+        theta[b] = torch.tensor([0.0, 0.0, 0.0])
+        obst[b, :, 0] = 10.0
+        obst[b, n % 4, :3] = torch.tensor([2.0, 0.4, 0.4])
+    th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+    obs = ob if spec.dynamic else None
+    planes = synthetic.to_planes(th, qd, ob, max(spec.num_obstacles, 1))
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(dev)):
+      for layout, (a, b_, c) in (("rows", (th, qd, ob)), ("planes", planes)):
+        c = c if spec.dynamic else None
+        v_full, l_full, d_full = fused.lagrangian_forward_backward(spec, a, b_, c, weights)
+        full_name = _cabi.last_kernel_name()
+        d_only = fused.lagrangian_backward(spec, a, b_, c, weights)
+        only_name = _cabi.last_kernel_name()
+        assert ("%s_tma," % layout) in full_name and "fwdbwd_" in full_name, full_name
+        assert ("%s_tma," % layout) in only_name and ",grad_" in only_name, only_name
+        assert torch.equal(d_only, d_full), "%s %s B=%d: gradient-only kernel differs from the full kernel" % (name, layout, B)
+        v_again, l_again, _ = fused.lagrangian_forward_backward(spec, a, b_, c, weights)
+        assert torch.equal(v_again, v_full) and torch.equal(l_again, l_full)
+  # a batch too small for the staged kernels: the request is served by the full direct-load kernel, sums discarded
+  theta, q_des, obst = synthetic.make_batch(100, seed=3)
+  th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+  _, _, d_full = fused.lagrangian_forward_backward(spec, th, qd, ob if spec.dynamic else None, lam.tolist())
+  d_only = fused.lagrangian_backward(spec, th, qd, ob if spec.dynamic else None, lam.tolist())
+  assert "fwdbwd_" in _cabi.last_kernel_name() and torch.equal(d_only, d_full)
+  # against the oracle
+  _, _, dref, _, truth = oracle_truth(ospec, theta, q_des, obst, lam)
+  grad_close(d_only.cpu().numpy(), dref, truth)
+
+
 def test_autograd_function_and_general_upstream_gradients(cuda_device):
   from ikl import fused, synthetic
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")

@@ -469,3 +469,56 @@ def test_unit_upstream_skips_the_scaling_pass_and_is_checked(cuda_device, monkey
   viol, loss = fused.FusedIkLagrangian.apply(th, q_des, obst, lam, spec, None, True)
   with pytest.raises(AssertionError):
     (2.0 * loss).backward()
+
+
+def test_training_steps_use_the_gradient_only_kernel(tmp_path, cuda_device):
+  """train_with_relaxation consumes only lagrange_loss.backward() (reference trainer.py:262-265), so its launches are the
+  gradient-only kernel unless --train_sums: the weights after a relaxation epoch must be bit-identical either way, the
+  autograd function must hand back NaN placeholders (never stale sums) and refuse gradients it cannot serve, and the dual
+  step / validation must still see real sums."""
+  from ikl import ConstraintSpec, synthetic, fused, _cabi
+  name = "cfg_joint_limits_and_4obs_dynamic"
+  fx = torch.load(os.path.join(GOLDEN, "dual_trajectory_%s.pt" % name))
+  from ikl.configs import write_config
+  from kinematics.dataset import IkDataset
+  from models.simple_network import SimpleNetwork
+  from scripts.options import Options
+  from scripts.trainer import IkLagrangeDualTrainer
+  cfg = config_json(name)
+  os.makedirs(str(tmp_path), exist_ok=True)
+  cfg_path = write_config(cfg, str(tmp_path / (name + ".json")))
+  datasets = (IkDataset(2048, 3, cfg), IkDataset(1024, 3, cfg))
+  finals = []
+  for extra in ((), ("--train_sums",)):
+    argv = ["--model_name", "t", "--config_file", cfg_path, "--log_dir", str(tmp_path), "--num_workers", "0", "--batch_size", "1024",
+            "--train_iters", "2", "--hidden_units", "32", "--train_dataset_size", "2048", "--val_dataset_size", "1024"]
+    tr = IkLagrangeDualTrainer(Options().parse(argv + list(extra)), datasets=datasets)
+    torch.manual_seed(0)
+    tr.model = SimpleNetwork(20, 3, hidden_units=32, depth=8, dropout=0.0).to(tr.device)
+    tr.optimizer = torch.optim.Adam(tr.model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    lam = tr.lambda_multipliers.clone() + 0.5
+    tr.train_with_relaxation(lam)
+    kernel = _cabi.last_kernel_name()
+    assert ("grad_" in kernel) == (not extra), kernel
+    lam2 = tr.update_multipliers(lam)
+    assert torch.isfinite(lam2).all() and ",fwd," in _cabi.last_kernel_name()
+    finals.append([p.detach().clone() for p in tr.model.parameters()] + [lam2])
+  for a, b in zip(*finals):
+    assert torch.equal(a, b)
+  # the autograd function itself
+  spec = ConstraintSpec.from_config(config_json(name), 3, 0.005, 1.0)
+  theta, q_des, obst = synthetic.make_batch(1024, seed=9, device="cuda:0")
+  lam = torch.linspace(0.5, 2.0, 16, device=cuda_device)
+  th = theta.clone().requires_grad_(True)
+  viol, loss = fused.FusedIkLagrangian.apply(th, q_des, obst, lam, spec, None, True, True)
+  assert torch.isnan(viol).all() and torch.isnan(loss)
+  loss.backward()
+  th2 = theta.clone().requires_grad_(True)
+  fused.FusedIkLagrangian.apply(th2, q_des, obst, lam, spec, None, True)[1].backward()
+  assert torch.equal(th.grad, th2.grad)
+  with pytest.raises(ValueError):
+    fused.FusedIkLagrangian.apply(th, q_des, obst, lam, spec, None, False, True)
+  th3 = theta.clone().requires_grad_(True)
+  viol, loss = fused.FusedIkLagrangian.apply(th3, q_des, obst, lam, spec, None, True, True)
+  with pytest.raises(RuntimeError):
+    viol.sum().backward()

@@ -51,12 +51,14 @@ def measure(args):
       if args.layouts and lname not in args.layouts.split(","):
         continue
       dth = torch.empty_strided(th.shape, th.stride(), dtype=torch.float32, device=dev)
-      for mode in ("fwdbwd_hostw", "fwdbwd_devw", "fwd"):
-        if args.quick and mode == "fwdbwd_devw":
+      for mode in ("fwdbwd_hostw", "fwdbwd_devw", "fwd", "grad_hostw", "grad_devw"):
+        if args.quick and mode in ("fwdbwd_devw", "grad_devw"):
           continue
         def call():
           if mode == "fwd":
             return fused.lagrangian_forward(spec, th, tg, ob if spec.dynamic else None, lam)
+          if mode.startswith("grad_"):      # gradient-only launch (ikl_lagrangian_backward): d/dtheta, no sums
+            return fused.lagrangian_backward(spec, th, tg, ob if spec.dynamic else None, lam if mode == "grad_hostw" else lam_dev, dtheta=dth)
           return fused.lagrangian_forward_backward(spec, th, tg, ob if spec.dynamic else None, lam if mode == "fwdbwd_hostw" else lam_dev, dtheta=dth)
         for _ in range(3):
           call()
