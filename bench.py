@@ -431,7 +431,48 @@ def strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms
   return res
 
 
-def train_step_metric(args, spec, dev, world, lam):
+def grad_allreduce_metric(args, dev, world, peer):
+  """The one exchange data-parallel training adds per step: the sum of the replicas' parameter gradients (83 203 floats for
+  the H=100 network + the 16 sums).  Timed as 50 back-to-back calls inside one CUDA graph (device time, max over ranks):
+  the peer-memory kernel of this repo (ikl_allreduce_sum_f32) against NCCL's all_reduce on the same buffer."""
+  import torch
+  import torch.distributed as dist
+  n = 83203 + 16
+  S = 50
+  buf = torch.zeros(n, device=dev)
+
+  def timed_graph(body, reps=10):
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      for _ in range(3):
+        body()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=side):
+        for _ in range(S):
+          body()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g.replay()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / (reps * S)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del g                                   # a captured NCCL collective must be gone before the process group is destroyed
+    return float(t.item()) * 1e3
+  res = {"elements": n, "calls_per_graph_replay": S}
+  if peer is not None:
+    res["peer_memory_kernel_us"] = timed_graph(lambda: peer.all_reduce_(buf))
+  res["nccl_all_reduce_us"] = timed_graph(lambda: dist.all_reduce(buf))
+  return res
+
+
+def train_step_metric(args, spec, dev, world, lam, peer=None):
   """Secondary metric of BASELINE.json on the configuration SURVEY 8(d) names: full dual-learning train steps/s with 2^24
   samples per step over ALL ranks (2^24 / N per rank: strong scaling), micro-batched.  Per micro-batch: SimpleNetwork (H=100,
   depth 8, dropout 0.05, 83 203 parameters; cuBLAS) forward with the last layer transposed so theta comes out as planes,
@@ -471,7 +512,7 @@ def train_step_metric(args, spec, dev, world, lam):
       viol, loss = fused.FusedIkLagrangian.apply(theta, q_pl[sl], ob_pl[sl], lam_dev, spec, lam, True)
       loss.backward()                                   # gradients of the sums add up over the micro-batches
       viol_sum.add_(viol.detach())
-    ikl_dist.all_reduce_gradients(model, extra=viol_sum)
+    ikl_dist.all_reduce_gradients(model, extra=viol_sum, peer=peer)
     opt.step()
 
   for _ in range(2):
@@ -508,7 +549,8 @@ def train_step_metric(args, spec, dev, world, lam):
           "fused_kernel_ms_per_micro_batch": kernel_ms, "fused_kernel_share": kernel_ms * n_micro / ms,
           "model": "SimpleNetwork(20->100x8->3, dropout 0.05, 83203 params) on cuBLAS + fused IK Lagrangian (planes, TMA) + Adam",
           "note": "bounded by the fp32 cuBLAS network (out of scope per north_star); the hot path of this repo is fused_kernel_share of the step",
-          "exchange": "one flat all-reduce of [83203 gradients | 16 violation sums] per step" if world > 1 else "none"}
+          "exchange": ("one flat all-reduce of [83203 gradients | 16 violation sums] per step, %s" % (
+              "one kernel over NVLink peer memory (ikl_allreduce_sum_f32)" if peer is not None else "NCCL")) if world > 1 else "none"}
 
 
 def small_batch_train_metric(args, spec, dev, lam):
@@ -839,9 +881,25 @@ def run_ours(args):
   if not args.skip_strong:
     strong = strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms_full=kernel_ms)
 
+  # gradient all-reduce of the data-parallel train step: one kernel over NVLink peer memory (--exchange nccl: NCCL)
+  peer_ar, grad_ar = None, None
+  if world > 1 and args.exchange == "peer" and exchange is not None:
+    ok = torch.ones(1, device=dev)
+    try:
+      from ikl.exchange import PeerAllReduce
+      peer_ar = PeerAllReduce(83203 + 16, device=dev)
+    except Exception as e:
+      ok.zero_()
+      exchange_note = (exchange_note or "") + " peer all-reduce unavailable (%s)" % (str(e)[:120],)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+      peer_ar = None
+  if world > 1 and not args.skip_strong:
+    grad_ar = grad_allreduce_metric(args, dev, world, peer_ar)
+
   train = None
   if not args.skip_train_step:
-    train = train_step_metric(args, spec, dev, world, lam)
+    train = train_step_metric(args, spec, dev, world, lam, peer=peer_ar)
 
   small = None
   if not args.skip_train_step and rank == 0 and world == 1:
@@ -853,6 +911,7 @@ def run_ours(args):
     line["train_step"] = train
     line["multi_gpu_check"] = multi_check
     line["strong_scaling"] = strong
+    line["grad_allreduce"] = grad_ar
     line["train_step_batch8"] = small
     line["context"] = extras
     if not args.skip_cpu and world == 1:

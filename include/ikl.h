@@ -156,6 +156,19 @@ IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const I
                                                     float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
                                                     const IklExchange* ex, void* stream);
 
+/* In-place sum over the ranks of a flat fp32 vector -- the one exchange data-parallel training adds to the reference's
+ * step: the replicas' parameter gradients after lagrange_loss.backward() (scripts/trainer.py:263-265; the reference is
+ * single-process).  ONE kernel over NVLink peer memory, same tagged-word protocol as the K-sum exchange above: every rank
+ * pushes its elements (fp32 bits + the launch's 32-bit sequence number in one 8-byte store) into every peer's mailbox,
+ * polls its own mailbox and adds the ranks' values in rank order, so the result is bit-identical everywhere.  No NCCL
+ * launch, capturable in a CUDA graph (the sequence number lives in the mailbox and is advanced by the kernel).  Meant for
+ * latency-bound sizes (the reference's networks have 2.5 k - 83 k parameters); every rank must call it with the same n in
+ * the same order.
+ *   ex->peers[r]  rank r's mailbox: ikl_allreduce_bytes(max_elems, world) bytes of symmetric memory, zero-filled once by
+ *                 its owner before anyone's first launch.  n <= max_elems. */
+size_t ikl_allreduce_bytes(int64_t max_elems, int32_t world);
+IklStatus ikl_allreduce_sum_f32(float* data, int64_t n, const IklExchange* ex, int64_t max_elems, void* stream);
+
 /* Gradient alone: d(sum_i w_i g_i)/d(theta) for arbitrary per-constraint weights w (for autograd:
  * w_i = grad(lagrange_loss) * lambda_i + grad(constraint_violations)_i).  Recomputes from the inputs -- nothing is
  * saved by the forward pass -- and replaces the autograd tape between lagrange_loss and the network output

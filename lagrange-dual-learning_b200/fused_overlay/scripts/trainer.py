@@ -133,10 +133,18 @@ class IkLagrangeDualTrainer(object):
     self.model = SimpleNetwork(20, self.opt.num_links, hidden_units=self.opt.hidden_units, depth=8, dropout=0.05).to(self.device)
     ikl_dist.broadcast_parameters(self.model)
     self.use_graph = bool(getattr(self.opt, "cuda_graph", False)) and self.device.type == "cuda"
-    if self.use_graph and self.world > 1 and os.environ.get("IKL_GRAPH_DISTRIBUTED", "0") != "1":
+    # Data-parallel runs sum the replicas' parameter gradients once per step.  On a CUDA box that is ONE kernel over NVLink
+    # peer memory (ikl.exchange.PeerAllReduce: no NCCL launch, capturable in the step graph); IKL_PEER_ALLREDUCE=0 keeps
+    # the NCCL all-reduce instead.
+    self._peer_allreduce = None
+    if self.world > 1 and self.device.type == "cuda" and os.environ.get("IKL_PEER_ALLREDUCE", "1") != "0":
+      from ikl.exchange import PeerAllReduce
+      self._peer_allreduce = PeerAllReduce(sum(p.numel() for p in self.model.parameters()), device=self.device)
+    if self.use_graph and self.world > 1 and self._peer_allreduce is None and os.environ.get("IKL_GRAPH_DISTRIBUTED", "0") != "1":
       # Capturing the flat NCCL all-reduce of the gradients inside the step graph is implemented (ikl/graph_step.py) but hung
-      # on the two-GPU box of this pool (tests/test_gpu_multi.py, round 2): off unless IKL_GRAPH_DISTRIBUTED=1.
-      print("NOTE: --cuda_graph under torch.distributed is experimental (set IKL_GRAPH_DISTRIBUTED=1); running eagerly")
+      # on the two-GPU box of this pool (profiles/r02/pytest_multi_graph_hang.log): with NCCL as the exchange the graph is
+      # off unless IKL_GRAPH_DISTRIBUTED=1.  The default exchange (peer-memory kernel) has no NCCL node and is graphed.
+      print("NOTE: --cuda_graph with the NCCL gradient all-reduce is experimental (set IKL_GRAPH_DISTRIBUTED=1); running eagerly")
       self.use_graph = False
     if self.use_graph and self.opt.batch_size % self.world != 0:
       print("NOTE: --cuda_graph needs --batch_size divisible by the world size (every rank replays the same graph); running eagerly")
@@ -311,7 +319,7 @@ class IkLagrangeDualTrainer(object):
       from ikl.graph_step import GraphedTrainStep
       self._graph_step = GraphedTrainStep(self.model, self.optimizer, self.spec, self.opt.batch_size // self.world, self.device,
                                           planes=bool(getattr(self.opt, "device_data", False)),
-                                          grad_only=not getattr(self.opt, "train_sums", False))
+                                          grad_only=not getattr(self.opt, "train_sums", False), peer_allreduce=self._peer_allreduce)
     if self._graph_step is not None:
       self._graph_step.set_multipliers(lamda)
     for ti, inputs in enumerate(self.train_loader):
@@ -332,7 +340,7 @@ class IkLagrangeDualTrainer(object):
         self._grad_only = False
       self.model.zero_grad()
       outputs["lagrange_loss"].backward()
-      ikl_dist.all_reduce_gradients(self.model)
+      ikl_dist.all_reduce_gradients(self.model, peer=self._peer_allreduce)
       self.optimizer.step()
 
   def update_multipliers(self, lamda):

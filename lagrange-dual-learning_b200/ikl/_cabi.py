@@ -61,6 +61,8 @@ _SIGNATURES = {
     "ikl_lagrangian_forward_backward_allreduce": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch),
                                                                  ctypes.POINTER(IklWeights), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                                  _c_i64, ctypes.POINTER(IklExchange), _c_vp]),
+    "ikl_allreduce_bytes": (ctypes.c_size_t, [_c_i64, _c_i32]),
+    "ikl_allreduce_sum_f32": (ctypes.c_int, [_c_vp, _c_i64, ctypes.POINTER(IklExchange), _c_i64, _c_vp]),
     "ikl_lagrangian_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
                                                _c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "ikl_dual_update": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_f, _c_i32, _c_vp, _c_vp]),

@@ -46,9 +46,11 @@ def broadcast_parameters(model, src=0):
       offset += n
 
 
-def all_reduce_gradients(model, extra=None):
+def all_reduce_gradients(model, extra=None, peer=None):
   """Sum parameter gradients (and, if given, the 1-D fp32 tensor `extra`, e.g. the K violation sums) over ranks in
-  one flat collective.  `extra` is updated in place.  No-op on a single process."""
+  one flat collective.  `extra` is updated in place.  No-op on a single process.
+  `peer` (ikl.exchange.PeerAllReduce): the sum runs as one kernel over NVLink peer memory instead of an NCCL all-reduce --
+  no NCCL launch, capturable in the step's CUDA graph, bit-identical on every rank."""
   if not is_distributed():
     return
   grads = [p.grad for p in model.parameters() if p.grad is not None]
@@ -58,7 +60,10 @@ def all_reduce_gradients(model, extra=None):
   if not pieces:
     return
   flat = torch.cat(pieces)
-  dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+  if peer is not None and flat.is_cuda and flat.dtype == torch.float32 and flat.numel() <= peer.max_elems:
+    peer.all_reduce_(flat)
+  else:
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
   offset = 0
   for g in grads:
     n = g.numel()

@@ -12,8 +12,10 @@ C ABI on the capturing stream like any other kernel.  The multipliers are read f
   planes=True       the static input buffers are structure-of-arrays planes and the network's last layer is evaluated
                     transposed (SimpleNetwork.forward_planes), so the TMA-staged planes kernel is the one in the graph --
                     what `--device_data` batches arrive as.
-  torch.distributed the flat all-reduce of the gradients (ikl.dist.all_reduce_gradients) is captured in the graph too
-                    (NCCL collectives are capturable); every rank replays the same sequence.
+  torch.distributed the flat all-reduce of the gradients (ikl.dist.all_reduce_gradients) is captured in the graph too; every
+                    rank replays the same sequence.  With peer_allreduce= (ikl.exchange.PeerAllReduce) it is ONE kernel
+                    over NVLink peer memory whose launch counter lives on the device -- no NCCL node in the graph (the
+                    captured NCCL all-reduce hung on this pool's two-GPU box, profiles/r02/pytest_multi_graph_hang.log).
 """
 import torch
 
@@ -22,7 +24,7 @@ from . import fused
 
 
 class GraphedTrainStep(object):
-  def __init__(self, model, optimizer, spec, batch_size, device, warmup=3, planes=False, grad_only=False):
+  def __init__(self, model, optimizer, spec, batch_size, device, warmup=3, planes=False, grad_only=False, peer_allreduce=None):
     if not torch.cuda.is_available():
       raise RuntimeError("CUDA graphs need a CUDA device")
     for group in optimizer.param_groups:
@@ -30,6 +32,7 @@ class GraphedTrainStep(object):
         raise ValueError("construct the optimizer with capturable=True (its step counter must live on the device)")
     self.model, self.optimizer, self.spec = model, optimizer, spec
     self.planes = bool(planes)
+    self.peer_allreduce = peer_allreduce  # ikl.exchange.PeerAllReduce: the gradient all-reduce as one peer-memory kernel in the graph
     self.grad_only = bool(grad_only)      # the step's launch is the gradient-only kernel; self.viol / self.loss are NaN placeholders
     dev = torch.device(device)
     B, K = int(batch_size), spec.num_constraints        # B: THIS rank's share of the batch
@@ -54,7 +57,7 @@ class GraphedTrainStep(object):
     viol, loss = fused.FusedIkLagrangian.apply(theta, self.q_des, self.obst, self.lam, self.spec, None, True, self.grad_only)
     self.optimizer.zero_grad(set_to_none=True)
     loss.backward()
-    ikl_dist.all_reduce_gradients(self.model)
+    ikl_dist.all_reduce_gradients(self.model, peer=self.peer_allreduce)
     self.optimizer.step()
     return viol, loss
 
@@ -94,6 +97,13 @@ class GraphedTrainStep(object):
     self.q_des.zero_()
     if self.obst is not None:
       self.obst.zero_()
+
+  def close(self):
+    """Drop the captured graph.  Needed only when the graph holds a captured NCCL all-reduce (peer_allreduce=None under
+    torch.distributed): torch.distributed.destroy_process_group() blocks for ever while such a graph is alive (measured on
+    this pool's two-GPU box, profiles/r02/debug_graph_dist_nccl.log: capture, replays and later eager collectives all work,
+    the teardown hangs) -- call close() first."""
+    self.graph = None
 
   def set_multipliers(self, lam):
     self.lam.copy_(lam)

@@ -188,7 +188,7 @@ def _graph_worker(rank, world, port, tmpdir):
       tr = make_trainer(NAME, d, fx, extra=extra)
       if tag == "graph":
         tr.optimizer = torch.optim.Adam(tr.model.parameters(), lr=tr.opt.optimizer_lr, betas=(0.9, 0.999), capturable=True)
-        assert tr.use_graph and tr.world == world
+        assert tr.use_graph and tr.world == world and tr._peer_allreduce is not None
       trainers.append(tr)
     for tr in trainers:
       for _ in range(3):
@@ -210,16 +210,91 @@ def _graph_worker(rank, world, port, tmpdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("IKL_GRAPH_DISTRIBUTED", "0") != "1",
-                    reason="needs two GPUs; experimental: the captured NCCL all-reduce hung on this pool's two-GPU box (round 2), "
-                           "so --cuda_graph under torch.distributed is off unless IKL_GRAPH_DISTRIBUTED=1")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(240)
 def test_two_gpu_cuda_graph_step_captures_the_gradient_all_reduce(tmp_path):
-  """--cuda_graph under torch.distributed: forward, fused Lagrangian, backward, the flat NCCL all-reduce of the gradients and
-  Adam are ONE graph replay per step on every rank; same lambda / weights as the eager two-rank run and as the reference's
-  single-process run on the same global batches."""
+  """--cuda_graph under torch.distributed: forward, gradient-only fused Lagrangian, backward, the all-reduce of the gradients
+  (one kernel over NVLink peer memory, ikl.exchange.PeerAllReduce -- the captured NCCL all-reduce hung on this pool's
+  two-GPU box) and Adam are ONE graph replay per step on every rank; same lambda / weights as the eager two-rank run and
+  as the reference's single-process run on the same global batches."""
   s = socket.socket()
   s.bind(("127.0.0.1", 0))
   port = s.getsockname()[1]
   s.close()
   mp.spawn(_graph_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
   assert (tmp_path / "graph_ok_0").exists() and (tmp_path / "graph_ok_1").exists()
+
+
+def _allreduce_worker(rank, world, port, tmpdir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  dev = torch.device("cuda", rank)
+  torch.cuda.set_device(dev)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+  try:
+    from ikl.exchange import PeerAllReduce
+    ar = PeerAllReduce(100000, device=dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for n in (1, 255, 2563, 83203, 100000, 0):
+      for rep in range(3):                       # consecutive launches alternate the mailbox parity
+        x = torch.randn(n, generator=g, device=dev) * (10.0 ** (rep - 1))
+        if n == 0:
+          assert ar.all_reduce_(x).numel() == 0
+          continue
+        parts = [torch.zeros_like(x) for _ in range(world)]
+        dist.all_gather(parts, x)
+        want = parts[0].clone()
+        for q in parts[1:]:
+          want += q                              # rank order, fp32: what the kernel adds
+        got = ar.all_reduce_(x.clone())
+        assert torch.equal(got, want), (n, rep)
+        both = [torch.zeros_like(got) for _ in range(world)]
+        dist.all_gather(both, got)
+        assert all(torch.equal(b, both[0]) for b in both), "the sum must be bit-identical on every rank"
+    with pytest.raises(ValueError):
+      ar.all_reduce_(torch.zeros(100001, device=dev))
+    # CUDA-graph capture: the launch counter lives in the mailbox and is advanced by the kernel, so replays pair up
+    x = torch.randn(2563, generator=g, device=dev)
+    buf = x.clone()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      ar.all_reduce_(buf)
+      buf.copy_(x)
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=side):
+        for _ in range(3):
+          ar.all_reduce_(buf)                    # buf <- world^3 * (sum of the ranks' x) over one replay
+    torch.cuda.current_stream(dev).wait_stream(side)
+    parts = [torch.zeros_like(x) for _ in range(world)]
+    dist.all_gather(parts, x)
+    want = parts[0].clone()
+    for q in parts[1:]:
+      want += q
+    for _ in range(4):
+      buf.copy_(x)
+      graph.replay()
+      torch.cuda.synchronize(dev)
+      torch.testing.assert_close(buf, want * float(world ** 2), rtol=1e-6, atol=1e-6)
+    # interleaved with NCCL collectives and eager launches afterwards
+    y = ar.all_reduce_(torch.ones(7, device=dev) * (rank + 1))
+    assert torch.equal(y, torch.full((7,), float(sum(range(1, world + 1))), device=dev))
+    open(os.path.join(tmpdir, "ar_ok_%d" % rank), "w").write("ok")
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(240)
+def test_peer_memory_all_reduce_of_a_flat_vector(tmp_path):
+  """ikl_allreduce_sum_f32: the gradient all-reduce of the data-parallel step as one kernel over NVLink peer memory -- equal
+  to the rank-order fp32 sum, bit-identical on every rank, ragged sizes, consecutive launches, CUDA-graph replays."""
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert (tmp_path / "ar_ok_0").exists() and (tmp_path / "ar_ok_1").exists()
