@@ -793,6 +793,31 @@ def run_ours(args):
                              "note": "theta (B,3), q_ee_desired (B,3), dynamic_obstacles (B,4,4) exactly as the reference's DataLoader "
                                      "hands them: 100 physical bytes per sample"}
     del dth_rows
+    # the launch of a TRAINING step (gradient only: scripts/trainer.py:262-265 consumes nothing but lagrange_loss.backward()),
+    # on the benchmark config and on the 4-static-obstacle config (32 B/sample: bound by the FP32 / ALU pipes, not by HBM)
+    try:
+      def timed20(fn):
+        for _ in range(3):
+          fn()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(20):
+          fn()
+        g1.record()
+        torch.cuda.synchronize()
+        return g0.elapsed_time(g1) / 20
+      go = {}
+      ms = timed20(lambda: fused.lagrangian_backward(spec, th_in, tg_in, ob_in, lam, dtheta=dtheta))
+      go["4obs_dynamic"] = {"kernel": _cabi.last_kernel_name(), "kernel_ms": ms, "with_sums_kernel_ms": kernel_ms,
+                            "frac_of_hbm_peak": ALGO_BYTES_PER_SAMPLE * B / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+      spec4 = ConstraintSpec.from_config(standard_config("cfg_joint_limits_and_4obs_static"), 3, GOOD_SLOPE, BAD_SLOPE)
+      ms_full = timed20(lambda: fused.lagrangian_forward_backward(spec4, th_in, tg_in, None, lam, dtheta=dtheta))
+      ms = timed20(lambda: fused.lagrangian_backward(spec4, th_in, tg_in, None, lam, dtheta=dtheta))
+      go["4obs_static"] = {"kernel": _cabi.last_kernel_name(), "kernel_ms": ms, "with_sums_kernel_ms": ms_full,
+                           "frac_of_hbm_peak": 32 * B / (ms * 1e-3) / 1e9 / measured_peak()[0], "algorithmic_bytes_per_sample": 32}
+      extras["gradient_only_launch"] = go
+    except Exception as e:
+      extras["gradient_only_launch"] = {"unavailable": str(e)[:200]}
     try:
       from oracle import ik_oracle as O
       Bg = 1 << 22

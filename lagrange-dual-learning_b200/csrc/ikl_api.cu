@@ -254,7 +254,7 @@ int prepare_lagrangian_params(const IklSpec* spec, const IklBatch* in, const flo
     // bulk-copy staged rows kernel: whole 512-row tiles of each tensor are single 16-byte aligned runs
     const char* e = getenv("IKL_ROWS_TMA");
     const bool want = !(e && e[0] == '0');
-    p.use_tma = want && in->batch >= kTmaTile && aligned16(in->theta) && aligned16(in->target) &&
+    p.use_tma = want && in->batch >= kTmaTile && in->batch < (int64_t(1) << 31) - 2 * kTmaTile && aligned16(in->theta) && aligned16(in->target) &&
                 (in->target_sb == 2 || in->target_sb == 3);
   }
   const int forced = forced_layout();

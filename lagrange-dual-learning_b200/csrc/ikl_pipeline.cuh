@@ -442,8 +442,9 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
   using L = TmaLayout<C>;
   constexpr int S = L::kStages;
   static_assert(kTmaTile % kTmaBox == 0, "a tile is a whole number of 256-sample boxes; thread v owns samples (2v, 2v+1): box = v / 128");
-  const long long B = p.batch;
-  const long long ntiles = (B + kTmaTile - 1) / kTmaTile;
+  // 32-bit indices: the host selects this kernel only for batches below 2^31 - 2 tiles (prepare_lagrangian_params)
+  const int B = (int)p.batch;
+  const int ntiles = (B + kTmaTile - 1) / kTmaTile;
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
   const unsigned drained0 = bar0 + 8 * S;
@@ -458,8 +459,8 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
   __syncthreads();
 
   // Stage layout: [half (2)][plane][256 samples]; each half is what one box of every group delivers.
-  auto issue = [&](long long tile, int stage) {      // one thread
-    const int b0 = (int)(tile * kTmaTile);
+  auto issue = [&](int tile, int stage) {            // one thread
+    const int b0 = tile * kTmaTile;
     const unsigned bar = bar0 + 8 * stage;
     const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
     mbar_expect_tx(bar, (unsigned)L::kStageBytes);    // boxes always deliver their full size (zero-filled past the batch end)
@@ -476,7 +477,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      const int t = (int)blockIdx.x + s * (int)gridDim.x;
       if (t < ntiles) issue(t, s);
     }
   }
@@ -484,9 +485,9 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
   int stage = 0;
   unsigned parity = 0;
   bool ready = false;                                  // the next tile's data was seen complete by an early probe
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (!ready) mbar_wait(bar0 + 8 * stage, parity);
-    const long long b = tile * kTmaTile + 2 * tid;
+    const int b = tile * kTmaTile + 2 * tid;
     const unsigned char* base = stage_mem + (size_t)stage * L::kStageBytes + (tid >> 7) * L::kHalfBytes + 8 * (tid & 127);
     f2 th[C::J], ob[C::NOB][3];
     int pl = 0;
@@ -508,7 +509,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
     __syncwarp();
     if (lane == 0) {
       const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
-      const long long next = tile + (long long)S * gridDim.x;
+      const int next = tile + S * (int)gridDim.x;
       if (last && next < ntiles) {
 #if IKL_PIPE_PROXY_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -520,7 +521,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
 #if IKL_EARLY_PROBE
     {
       const int nstage = stage + 1 == S ? 0 : stage + 1;
-      ready = (tile + gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
+      ready = (tile + (int)gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
     }
 #endif
     if (b < B) body.pair(th, tx, ty, ob, b, b + 1);
@@ -627,7 +628,8 @@ template <class C, class Body>
 __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& body, unsigned char* stage_mem, unsigned long long* bars, int r) {
   using L = RowsTmaLayout<C>;
   constexpr int S = L::kStages;
-  const long long ntiles = p.batch / kTmaTile;       // full tiles only; the caller evaluates the ragged tail
+  // 32-bit tile indices: the host selects this kernel only for batches below 2^31 (prepare_lagrangian_params)
+  const int ntiles = (int)(p.batch / kTmaTile);      // full tiles only; the caller evaluates the ragged tail
   const int tid = threadIdx.x, lane = tid & 31;
   const int tg_sb = (int)p.tg_sb;                    // 2 or 3 (checked on the host)
   const unsigned bar0 = smem_u32(bars);              // S "full" barriers, then S "drained" barriers
@@ -642,8 +644,8 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
   }
   __syncthreads();
 
-  auto issue = [&](long long tile, int stage) {      // one thread
-    const long long b0 = tile * kTmaTile;
+  auto issue = [&](int tile, int stage) {            // one thread
+    const long long b0 = (long long)tile * kTmaTile;
     const unsigned bar = bar0 + 8 * stage;
     const unsigned dst = smem_u32(stage_mem + (size_t)stage * L::kStageBytes);
     const unsigned tg_bytes = (unsigned)(kTmaTile * 4) * (unsigned)tg_sb;
@@ -656,7 +658,7 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      const int t = (int)blockIdx.x + s * (int)gridDim.x;
       if (t < ntiles) issue(t, s);
     }
   }
@@ -664,7 +666,7 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
   int stage = 0;
   unsigned parity = 0;
   bool ready = false;                                  // the next tile's data was seen complete by an early probe
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (!ready) mbar_wait(bar0 + 8 * stage, parity);
     const unsigned char* st = stage_mem + (size_t)stage * L::kStageBytes;
     f2 th[C::J], ob[C::NOB][3];
@@ -693,7 +695,7 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
     __syncwarp();
     if (lane == 0) {
       const bool last = mbar_arrive_is_last(drained0 + 8 * stage);
-      const long long next = tile + (long long)S * gridDim.x;
+      const int next = tile + S * (int)gridDim.x;
       if (last && next < ntiles) {
 #if IKL_PIPE_PROXY_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -705,10 +707,10 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
 #if IKL_EARLY_PROBE
     {
       const int nstage = stage + 1 == S ? 0 : stage + 1;
-      ready = (tile + gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
+      ready = (tile + (int)gridDim.x < ntiles) && mbar_test(bar0 + 8 * nstage, nstage == 0 ? parity ^ 1u : parity);
     }
 #endif
-    const long long bA = tile * kTmaTile + tid;
+    const long long bA = (long long)tile * kTmaTile + tid;
     body.pair(th, tx, ty, ob, bA, bA + kThreads);
     body.tile_done();
     if (++stage == S) {
