@@ -20,6 +20,8 @@
 // statistics of scripts/evaluation/visualize_ik_solutions.py:97-119).
 #pragma once
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "ikl_common.h"
@@ -643,6 +645,19 @@ inline int grid_sms() {
   const int n = sm_count() - reserved_sms();
   return n > 0 ? n : 1;
 }
+// Blocks per SM a staged kernel's persistent grid is sized for.  The kernels without obstacles need so few registers that
+// four or five blocks fit an SM, but the ones that also WRITE d/dtheta run best with three (same-run sweep at 2^24 samples,
+// profiles/r02/kernel_table_block_cap.jsonl: unconstrained planes fwd+bwd 0.099 -> 0.090 ms, gradient-only 0.095 -> 0.084 ms =
+// 98 % of the HBM peak; rows gradient-only 0.109 -> 0.093 ms; joint limits alike); forward-only launches keep every block
+// they can get (0.066 vs 0.071 ms).  IKL_GRID_BLOCKS_PER_SM=n overrides the rule (measurements).
+template <class C>
+inline int staged_blocks_per_sm(int resident) {
+  static const int forced = [] { const char* e = getenv("IKL_GRID_BLOCKS_PER_SM"); return e && *e ? atoi(e) : -1; }();
+  if (forced > 0) return resident < forced ? resident : forced;
+  if (forced == 0) return resident;
+  constexpr int cap = (C::GRAD && C::NOBS == 0) ? 3 : 1 << 20;
+  return resident < cap ? resident : cap;
+}
 
 // Resident blocks per SM of a kernel with `smem` bytes of dynamic shared memory, cached per (kernel instantiation, device):
 // the opt-in to more than 48 KiB of dynamic shared memory is a per-device function attribute, so a process that drives
@@ -682,7 +697,7 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       if (e != cudaSuccess) return e;
       long long tiles = (p.batch + kTmaTile - 1) / kTmaTile;
       if (tiles < 1) tiles = 1;
-      long long grid = (long long)grid_sms() * tma_blocks_per_sm;
+      long long grid = (long long)grid_sms() * staged_blocks_per_sm<C>(tma_blocks_per_sm);
       if (grid > tiles) grid = tiles;
       if (grid > max_blocks) grid = max_blocks;
       set_last_kernel_name(name);
@@ -700,7 +715,7 @@ cudaError_t launch_cfg(const LagrangianParams& p, cudaStream_t stream, int max_b
       if (e != cudaSuccess) return e;
       long long tiles = p.batch / kTmaTile;
       if (tiles < 1) tiles = 1;
-      long long grid = (long long)grid_sms() * rows_blocks_per_sm;
+      long long grid = (long long)grid_sms() * staged_blocks_per_sm<C>(rows_blocks_per_sm);
       if (grid > tiles) grid = tiles;
       if (grid > max_blocks) grid = max_blocks;
       set_last_kernel_name(name);
