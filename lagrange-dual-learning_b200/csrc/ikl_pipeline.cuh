@@ -78,6 +78,10 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const TensorMap* tm, i
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
+// Programmatic dependent launch (see launch_staged): no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kTmaBox = 256;                           // samples per TMA box (the hardware limit per box dimension)
 constexpr int kTmaBoxBytes = kTmaBox * 4;
 
@@ -457,6 +461,7 @@ __device__ __forceinline__ void run_planes_pipe(const LagrangianParams& p, Body&
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();                                         // the previous kernel on the stream is complete: global memory may be touched
 
   // Stage layout: [half (2)][plane][256 samples]; each half is what one box of every group delivers.
   auto issue = [&](int tile, int stage) {            // one thread
@@ -564,6 +569,8 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_p
   __shared__ double s_warp[kWarps][kMaxK];
   __shared__ float s_lam1[kMaxK];
   __shared__ float2 s_lam_pairs[3][kMaxObstPairs];
+  pdl_launch_dependents();
+  if constexpr (C::DEVW) pdl_wait();           // the multipliers are read from global memory right away
   if constexpr (C::DEVW) {
     if (threadIdx.x < C::K) {
       const float l = __ldg(p.w_dev + threadIdx.x);
@@ -643,6 +650,7 @@ __device__ __forceinline__ void run_rows_pipe(const LagrangianParams& p, Body& b
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();                                         // the previous kernel on the stream is complete: global memory may be touched
 
   auto issue = [&](int tile, int stage) {            // one thread
     const long long b0 = (long long)tile * kTmaTile;
@@ -730,6 +738,8 @@ __global__ void __launch_bounds__(kThreads, staged_min_blocks<C>()) lagrangian_r
   __shared__ double s_warp[kWarps][kMaxK];
   const int r = L::kPermuted ? ((threadIdx.x >> 1) & 3) : 0;
   constexpr bool kSmemWeights = C::GRAD && (C::DYN || C::DEVW);
+  pdl_launch_dependents();
+  if constexpr (C::DEVW) pdl_wait();           // the multipliers are read from global memory right away
   if constexpr (kSmemWeights) {
     if (threadIdx.x < 4 * kMaxK) {
       const int rr = threadIdx.x / kMaxK, i = threadIdx.x % kMaxK;
