@@ -458,8 +458,17 @@ __device__ __forceinline__ f2 ldg_stream_f2(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
   return r;
 }
+// IKL_STORE_CS=1: d/dtheta is stored with the evict-first (.cs) policy instead of L1::no_allocate.  Measured and rejected
+// (profiles/r02/kernel_table_cache_policy.jsonl): 0.2116 -> 0.2136 ms on the benchmark kernel, nothing elsewhere.
+#ifndef IKL_STORE_CS
+#define IKL_STORE_CS 0
+#endif
 __device__ __forceinline__ void stg_stream_f2(float* p, f2 v) {
+#if IKL_STORE_CS
+  asm volatile("st.global.cs.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
   asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
 }
 
 template <class C>

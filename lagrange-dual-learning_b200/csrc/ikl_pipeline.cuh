@@ -70,13 +70,34 @@ __device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
 }
 // Tiled TMA loads: one instruction moves a {256 samples x all planes of a group} box; rows past the end of the batch
 // are zero-filled by the hardware, so ragged last tiles need no special case.
+// IKL_TMA_EVICT_FIRST=1: the staged loads carry an L2 evict-first policy (the batch is streamed once and never re-read).
+// Measured and rejected (profiles/r02/kernel_table_cache_policy.jsonl, same-run A/B at 2^24): the benchmark kernel gets 8 %
+// SLOWER (0.2116 -> 0.2280 ms fwd+bwd, 0.204 -> 0.223 gradient-only), forward-only and the light kernels do not move.
+#ifndef IKL_TMA_EVICT_FIRST
+#define IKL_TMA_EVICT_FIRST 0
+#endif
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const TensorMap* tm, int x, int y, unsigned bar) {
+#if IKL_TMA_EVICT_FIRST
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+               "l"(tm), "r"(x), "r"(y), "r"(bar), "l"(l2_evict_first_policy()) : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                "l"(tm), "r"(x), "r"(y), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const TensorMap* tm, int x, int y, int z, unsigned bar) {
+#if IKL_TMA_EVICT_FIRST
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar), "l"(l2_evict_first_policy()) : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+#endif
 }
 // Programmatic dependent launch (see launch_staged): no-ops when the kernel was launched without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
