@@ -217,19 +217,23 @@ __device__ __forceinline__ void block_finalize(const LagrangianParams& p, double
   __threadfence();
   {
     const int i = tid % kMaxK, part = tid / kMaxK;
-    // same order of additions as a plain loop, but eight loads in flight at a time: with ~300 blocks this chain of dependent
-    // L2 round trips was ~3 us of every launch -- nothing at 2^24 samples, 10 % of a launch on a 2^21-sample shard (strong scaling)
+    // same order of additions as a plain loop, but up to twenty loads in flight at a time (a grid of 296 blocks is ONE batch per
+    // thread): as a chain of dependent L2 round trips this was ~3 us of every launch, in batches of eight still three round
+    // trips -- nothing at 2^24 samples, several per cent of a launch on a 2^21-sample shard (strong scaling).  Slots past the
+    // grid contribute +0.0, which leaves the sum's bits alone.
     double v = 0.0;
     if (i < K) {
-      unsigned blk = part;
-      for (; blk + 7 * kFinalParts < gridDim.x; blk += 8 * kFinalParts) {
-        double t[8];
+      constexpr int kBatch = 20;
+      for (unsigned blk = part; blk < gridDim.x; blk += kBatch * kFinalParts) {
+        double t[kBatch];
 #pragma unroll
-        for (int uu = 0; uu < 8; ++uu) t[uu] = __ldcg(p.partials + (size_t)(blk + uu * kFinalParts) * kMaxK + i);
+        for (int uu = 0; uu < kBatch; ++uu) {
+          const unsigned b = blk + uu * kFinalParts;
+          t[uu] = b < gridDim.x ? __ldcg(p.partials + (size_t)b * kMaxK + i) : 0.0;
+        }
 #pragma unroll
-        for (int uu = 0; uu < 8; ++uu) v += t[uu];
+        for (int uu = 0; uu < kBatch; ++uu) v += t[uu];
       }
-      for (; blk < gridDim.x; blk += kFinalParts) v += __ldcg(p.partials + (size_t)blk * kMaxK + i);
     }
     s_fin[part][i] = v;
   }
