@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IKL_ABI_VERSION 3
+#define IKL_ABI_VERSION 4
 #define IKL_MAX_LINKS 3        /* reference trainer supports 3 (scripts/trainer.py:177-180); 2 is templated too */
 #define IKL_MAX_OBSTACLES 4    /* reference hard-wires (B,4,4): scripts/trainer.py:218, kinematics/dataset.py:80 */
 #define IKL_MAX_CONSTRAINTS (1 + IKL_MAX_LINKS + IKL_MAX_LINKS * IKL_MAX_OBSTACLES)   /* 16 */

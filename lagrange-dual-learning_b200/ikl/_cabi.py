@@ -16,7 +16,7 @@ MAX_LINKS = 3
 MAX_OBSTACLES = 4
 MAX_CONSTRAINTS = 1 + MAX_LINKS + MAX_LINKS * MAX_OBSTACLES
 MAX_RANKS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 IKL_OK, IKL_ERR_INVALID_ARGUMENT, IKL_ERR_UNSUPPORTED, IKL_ERR_CUDA = 0, 1, 2, 3
 

@@ -1023,6 +1023,16 @@ def test_two_links_and_non_unit_link_lengths(J, lengths, name, cuda_device, monk
   diff = np.abs(grads["strided"] - grads["planes"]).max(axis=1)
   assert np.quantile(diff, 0.99) <= 2e-6 * scale and diff.max() <= 1e-4 * scale
   monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  # the gradient-only specialisations of these families (what a training step launches): same d/dtheta bits, staged kernels
+  from ikl import synthetic
+  th, qd, ob = theta.to(cuda_device), q_des.to(cuda_device), obst.to(cuda_device)
+  for layout, args in (("rows", (th, qd, ob)), ("planes", synthetic.to_planes(th, qd, ob, max(spec.num_obstacles, 1)))):
+    o = args[2] if spec.dynamic else None
+    _, _, d_full = fused.lagrangian_forward_backward(spec, args[0], args[1], o, lam.tolist())
+    d_only = fused.lagrangian_backward(spec, args[0], args[1], o, lam.tolist())
+    kname = _cabi.last_kernel_name()
+    assert (layout + "_tma,") in kname and ",grad_hostw," in kname and tag in kname, kname
+    assert torch.equal(d_only, d_full), kname
   # the function-level FK agrees with the same geometry
   from ikl import ops
   tips = ops.fk_forward_kinematics(theta.to(cuda_device), lengths)
