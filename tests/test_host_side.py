@@ -127,7 +127,12 @@ def _worker(rank, world, port, tmpdir):
     net.zero_grad()
     out["lagrange_loss"].backward()
     viol = out["constraint_violations"].detach().clone()
-    D.all_reduce_gradients(net, extra=viol)
+    class NeverUsed(object):                         # a peer-memory all-reduce serves CUDA float32 buffers only: CPU tensors go to the group
+      max_elems = 1 << 30
+
+      def all_reduce_(self, flat):
+        raise AssertionError("the peer all-reduce must not be handed a CPU tensor")
+    D.all_reduce_gradients(net, extra=viol, peer=NeverUsed())
     # single-process truth on the whole batch
     ref_net = SimpleNetwork(20, 3, hidden_units=8, depth=2, dropout=0.0)
     ref_net.load_state_dict(net.state_dict())

@@ -7,6 +7,7 @@ mkdir -p $O
 python -m pytest tests -m gpu -q --timeout 900 > $O/pytest_gpu_final.log 2>&1; echo "pytest exit $? ($(date -u +%Y-%m-%dT%H:%M:%SZ))" >> $O/pytest_gpu_final.log
 tail -4 $O/pytest_gpu_final.log
 python __graft_entry__.py smoke > $O/smoke_final.log 2>&1; echo "smoke exit $?" >> $O/smoke_final.log; tail -2 $O/smoke_final.log
+python tools/parity_report.py --out $O/parity_report_final.json > $O/parity_report_final.log 2>&1; echo "parity exit $?" >> $O/parity_report_final.log
 python tools/kernel_bench.py --iters 30 > $O/kernel_table_final.jsonl 2> $O/kernel_table_final.err
 python bench.py --steps 20 --warmup 3 > $O/bench_final.json 2> $O/bench_final.err; echo "bench exit $?" >> $O/bench_final.err
 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
