@@ -36,6 +36,7 @@ UNIT = "samples/s"
 ALGO_BYTES_PER_SAMPLE = 80          # read theta 12 + target xy 8 + 4x(x,y,r) 48, write dtheta 12
 CONFIG_NAME = "cfg_joint_limits_and_4obs_dynamic"
 GOOD_SLOPE, BAD_SLOPE = 0.005, 1.0   # scripts/experiments/ik_threelink_obs4_dyn.sh:15-16
+MULTIPLIER_LR = 1e-4                 # scripts/options.py:17 (the reference's default dual step size)
 
 
 def bind_to_gpu_numa_node(index):
@@ -373,16 +374,16 @@ def strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms
   out = torch.empty(K + 1, dtype=torch.float32, device=dev)
   S = 50                                   # steps per graph replay
 
-  def timed_graph(body, reps=10):
+  def timed_graph(body, reps=10, last_body=None):
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-      for _ in range(3):
-        body()
+      for k in range(3):
+        (last_body if (last_body is not None and k == 2) else body)()
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g, stream=side):
-        for _ in range(S):
-          body()
+        for k in range(S):
+          (last_body if (last_body is not None and k == S - 1) else body)()
     torch.cuda.current_stream(dev).wait_stream(side)
     g.replay()
     if world > 1:
@@ -407,6 +408,18 @@ def strong_scaling_metric(args, spec, dev, world, rank, lam, exchange, kernel_ms
   elif exchange is not None:
     step_ms = timed_graph(lambda: fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out, exchange=exchange))
     res["exchange"] = "inside the fused kernel: NVLink peer stores of the 16 fp64 sums + flag, last block pulls and adds"
+    if args.exchange == "epoch":
+      # the bench line's own form: a graph replay is one dual step of S batches; the sums stay local (float64 running sum) until
+      # the S-th launch, which exchanges the running sums and moves lambda in the same kernel
+      res["per_step_exchange_ms_per_step"] = step_ms
+      acc = torch.zeros(K, dtype=torch.float64, device=dev)
+      lam_dev = torch.tensor(lam, device=dev)
+      closer = fused.DualStep(lam_dev, MULTIPLIER_LR, out=torch.empty_like(lam_dev), exchange=exchange)
+      step_ms = timed_graph(lambda: fused.lagrangian_forward_backward(spec, th, tg, ob, lam, viol_accum=acc, dtheta=dth, out=out),
+                            last_body=lambda: fused.lagrangian_forward_backward(spec, th, tg, ob, lam, viol_accum=acc, dtheta=dth, out=out,
+                                                                                close_epoch=closer))
+      res["exchange"] = ("once per dual step of %d batches: the closing launch exchanges the ranks' float64 running sums over NVLink peer memory "
+                         "and moves lambda in the same kernel; `per_step_exchange_ms_per_step` = the 16 sums all-reduced inside EVERY launch" % S)
   else:
     def body():
       fused.lagrangian_forward_backward(spec, th, tg, ob, lam, dtheta=dth, out=out)
@@ -651,7 +664,7 @@ def run_ours(args):
   # The K sums are all-reduced INSIDE the fused kernel over NVLink peer memory (ikl.exchange.PeerExchange, include/ikl.h
   # IklExchange); --exchange nccl keeps the round-1 form (one asynchronous 64-byte NCCL all-reduce per step) for comparison.
   exchange, exchange_note = None, None
-  if world > 1 and args.exchange == "peer":
+  if world > 1 and args.exchange in ("epoch", "peer"):
     ok = torch.ones(1, device=dev)
     try:
       from ikl.exchange import PeerExchange
@@ -676,9 +689,22 @@ def run_ours(args):
   accum = torch.zeros(K, dtype=torch.float64, device=dev)
   lam_dev = torch.tensor(lam, device=dev)
 
+  lam_next = torch.empty_like(lam_dev)
+  # Default (--exchange epoch): the timed steps are the batches of ONE dual step (scripts/trainer.py:267-286 sums the K-vectors
+  # of every batch and moves lambda once).  Every step adds its 16 sums into the rank's float64 running sum; the LAST step of
+  # the region is launched through ikl_lagrangian_forward_backward_dual_step: that same kernel exchanges the running sums over
+  # NVLink peer memory -- once per epoch, which is when the path needs global sums -- and writes the new lambda.  At N = 1 the
+  # closing launch only fuses the lambda update.  --exchange peer: a per-step all-reduce inside every launch instead.
+  epoch_mode = args.exchange == "epoch" and (world == 1 or exchange is not None)
+  closer = fused.DualStep(lam_dev, MULTIPLIER_LR, out=lam_next, exchange=exchange) if epoch_mode else None
+
   pending = []
 
-  def step():
+  def step(last=False):
+    if epoch_mode:
+      viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta,
+                                                        close_epoch=closer if last else None)
+      return viol, loss
     if exchange is not None:          # ONE kernel: compute + all-reduce of the 16 sums over peer memory; viol is global
       viol, loss, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=accum, dtheta=dtheta, exchange=exchange)
       return viol, loss
@@ -701,21 +727,45 @@ def run_ours(args):
     torch.cuda.synchronize()
 
   sampler = ClockSampler(local_rank) if rank == 0 else None
-  for _ in range(max(args.warmup, 3)):
-    step()
+  n_warm = max(args.warmup, 3)
+  for i in range(n_warm):
+    step(last=(i == n_warm - 1))   # the warm-up is an epoch of its own: the closing launch is warm too
   drain()
+  accum.zero_()
   barrier()
   launches0 = _cabi.launch_count()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   t_wall0 = time.time()
   ev0.record()
-  for _ in range(args.steps):
-    viol, loss = step()
+  for i in range(args.steps):
+    viol, loss = step(last=(i == args.steps - 1))
   drain()                          # the timed region ends when every all-reduce has completed
   ev1.record()
   barrier()
   t_wall1 = time.time()
   launches = _cabi.launch_count() - launches0
+  epoch_check = None
+  if epoch_mode:
+    # what the timed region computed: the GLOBAL epoch sums in `accum` and the new lambda, identical on every rank
+    local_epoch = torch.zeros(K, dtype=torch.float64, device=dev)
+    one, _, _ = fused.lagrangian_forward_backward(spec, th_in, tg_in, ob_in, lam, viol_accum=local_epoch, dtheta=dtheta)
+    parts = [local_epoch.clone()]
+    if world > 1:
+      parts = [torch.zeros_like(local_epoch) for _ in range(world)]
+      dist.all_gather(parts, local_epoch)
+    want = args.steps * torch.stack(parts).sum(0)
+    rel = float(((accum - want).abs() / (args.steps * torch.stack(parts).abs().sum(0)).clamp(min=1e-30)).max())
+    lam_want = fused.dual_update(lam_dev, accum, MULTIPLIER_LR)
+    lams = [lam_next.clone()]
+    if world > 1:
+      lams = [torch.zeros_like(lam_next) for _ in range(world)]
+      dist.all_gather(lams, lam_next)
+    epoch_check = {"epoch_sums_rel_err_vs_steps_x_f64_sum_of_rank_sums": rel,
+                   "lambda_equals_ikl_dual_update_of_the_epoch_sums": bool(torch.equal(lam_next, lam_want)),
+                   "lambda_bit_identical_across_ranks": bool(all(torch.equal(l, lams[0]) for l in lams)),
+                   "lambda_moved": bool((lam_next != lam_dev).any().item()), "multiplier_lr": MULTIPLIER_LR}
+    epoch_check["ok"] = bool(rel <= 1e-9 and epoch_check["lambda_equals_ikl_dual_update_of_the_epoch_sums"] and
+                             epoch_check["lambda_bit_identical_across_ranks"] and epoch_check["lambda_moved"])
   kernel_name = _cabi.last_kernel_name()
   ms_total = ev0.elapsed_time(ev1)
   t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -764,8 +814,13 @@ def run_ours(args):
         "config": {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
                    "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
                    "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
+                   "step": ("one batch of a dual step (scripts/trainer.py:267-286): fused fwd+bwd launch, 16 sums added to the rank's float64 running "
+                            "sum; the region's LAST launch closes the epoch in the same kernel (exchange of the running sums + lambda update)"
+                            if epoch_mode else "fused fwd+bwd launch with the 16 sums all-reduced every step"),
                    "parallelism": ("single GPU" if world == 1 else
-                                   "batch shard per GPU; the 16 violation sums all-reduced inside the fused kernel over NVLink peer memory" if exchange is not None else
+                                   "batch shard per GPU; running sums exchanged ONCE per dual step, inside the closing launch, over NVLink peer "
+                                   "memory (ikl_lagrangian_forward_backward_dual_step); no other collective in the timed region" if epoch_mode else
+                                   "batch shard per GPU; the 16 violation sums all-reduced inside the fused kernel over NVLink peer memory, every step" if exchange is not None else
                                    "batch shard per GPU; asynchronous NCCL all-reduce of the 16 violation sums per step (overlaps the next step's kernel)")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
@@ -774,6 +829,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "native_lib": _cabi.loaded_path(),
     }
+    if epoch_check is not None:
+      line["dual_step_check"] = epoch_check
 
   # ---- context numbers (rank 0, N = 1): the reference's own tensor layout, and the reference's eager path on this GPU
   extras = {}
@@ -908,7 +965,7 @@ def run_ours(args):
 
   # gradient all-reduce of the data-parallel train step: one kernel over NVLink peer memory (--exchange nccl: NCCL)
   peer_ar, grad_ar = None, None
-  if world > 1 and args.exchange == "peer" and exchange is not None:
+  if world > 1 and args.exchange in ("epoch", "peer") and exchange is not None:
     ok = torch.ones(1, device=dev)
     try:
       from ikl.exchange import PeerAllReduce
@@ -971,8 +1028,9 @@ def main():
   ap.add_argument("--skip-cpu", action="store_true")
   ap.add_argument("--skip-multi-check", action="store_true")
   ap.add_argument("--skip-strong", action="store_true")
-  ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                  help="N > 1: how the 16 sums are all-reduced (peer = inside the fused kernel over NVLink peer memory)")
+  ap.add_argument("--exchange", default="epoch", choices=["epoch", "peer", "nccl"],
+                  help="when the 16 sums become global: epoch = once per dual step, inside the closing launch, over NVLink peer memory "
+                       "(what update_multipliers needs); peer = all-reduced inside EVERY launch; nccl = asynchronous NCCL all-reduce per step")
   ap.add_argument("--strong-total-log2", type=int, default=24, help="total batch of the strong-scaling measurement (sharded over the ranks)")
   ap.add_argument("--compare-nccl", action="store_true", help="strong scaling: also time kernel + NCCL all-reduce in a CUDA graph")
   ap.add_argument("--train-total-log2", type=int, default=24, help="samples per train step over ALL ranks (SURVEY 8d), micro-batched")

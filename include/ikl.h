@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IKL_ABI_VERSION 4
+#define IKL_ABI_VERSION 5
 #define IKL_MAX_LINKS 3        /* reference trainer supports 3 (scripts/trainer.py:177-180); 2 is templated too */
 #define IKL_MAX_OBSTACLES 4    /* reference hard-wires (B,4,4): scripts/trainer.py:218, kinematics/dataset.py:80 */
 #define IKL_MAX_CONSTRAINTS (1 + IKL_MAX_LINKS + IKL_MAX_LINKS * IKL_MAX_OBSTACLES)   /* 16 */
@@ -155,6 +155,35 @@ IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const I
                                                     void* workspace, float* viol_out, float* loss_out, double* viol_accum,
                                                     float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
                                                     const IklExchange* ex, void* stream);
+
+/* ---- the launch that CLOSES a dual step: compute + collective + multiplier update in one kernel -----------------------
+ * update_multipliers (scripts/trainer.py:267-286) sums the K-vectors of every validation batch and then moves lambda ONCE.
+ * So a data-parallel dual step needs the global sums once per epoch, not once per batch: the earlier batches of the epoch
+ * are plain ikl_lagrangian_forward[_backward] launches that add into the rank's LOCAL viol_accum, and the epoch's last batch
+ * is launched through one of the two entry points below.  The block that finishes that launch's reduction
+ *   1. adds the launch's K sums to viol_accum (this rank's running sum of the epoch),
+ *   2. with ex (world > 1) exchanges those K running sums over NVLink peer memory -- the tagged-word protocol described
+ *      above, ONE exchange per epoch -- and adds the ranks' vectors in rank order,
+ *   3. leaves the GLOBAL epoch sums in viol_accum (bit-identical on every rank) and,
+ *   4. with dual, writes lam_out[i] = max(0, lam_in[i] + multiplier_lr * (float)viol_accum[i]) -- the arithmetic of
+ *      ikl_dual_update, so lambda is bit-identical on every rank and equal to what the separate kernel would give.
+ * viol_out / loss_out hold this launch's LOCAL sums and Lagrangian, evaluated with the multipliers of BEFORE the update
+ * (w; w->device and dual->lam_out may be the same buffer).  viol_accum is required; ex may be NULL (single process: the
+ * dual update is simply fused into the last forward launch); dual may be NULL (only close the epoch's sum).
+ * Every rank must close the epoch with the same kind of launch (its batch may be empty). */
+typedef struct IklDualStep {
+  const float* lam_in;            /* [K] device */
+  float* lam_out;                 /* [K] device; may alias lam_in */
+  float multiplier_lr;            /* opt.multiplier_lr (scripts/options.py) */
+} IklDualStep;
+
+IklStatus ikl_lagrangian_forward_dual_step(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
+                                           float* viol_out, float* loss_out, double* viol_accum, const IklExchange* ex,
+                                           const IklDualStep* dual, void* stream);
+IklStatus ikl_lagrangian_forward_backward_dual_step(const IklSpec* spec, const IklBatch* in, const IklWeights* w,
+                                                    void* workspace, float* viol_out, float* loss_out, double* viol_accum,
+                                                    float* dtheta, int64_t dtheta_sb, int64_t dtheta_sj,
+                                                    const IklExchange* ex, const IklDualStep* dual, void* stream);
 
 /* In-place sum over the ranks of a flat fp32 vector -- the one exchange data-parallel training adds to the reference's
  * step: the replicas' parameter gradients after lagrange_loss.backward() (scripts/trainer.py:263-265; the reference is

@@ -267,10 +267,13 @@ namespace {
 
 IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out, float* loss_out,
               double* viol_accum, float* q_ee_out, float* err_sq_out, float* dtheta, int64_t dt_sb, int64_t dt_sj, bool grad,
-              void* stream, const IklExchange* ex = nullptr, bool sums = true) {
+              void* stream, const IklExchange* ex = nullptr, bool sums = true, bool close_epoch = false,
+              const IklDualStep* dual = nullptr) {
   IklStatus st = validate(spec, in, w, workspace, viol_out, loss_out);
   if (st != IKL_OK) return st;
   if (grad && in->batch > 0 && !dtheta) return IKL_ERR_INVALID_ARGUMENT;
+  if (close_epoch && !viol_accum) return IKL_ERR_INVALID_ARGUMENT;
+  if (dual && (!close_epoch || !dual->lam_in || !dual->lam_out)) return IKL_ERR_INVALID_ARGUMENT;
   if (ex) {
     if (ex->world < 1 || ex->world > IKL_MAX_RANKS || ex->rank < 0 || ex->rank >= ex->world) return IKL_ERR_INVALID_ARGUMENT;
     for (int r = 0; r < ex->world; ++r)
@@ -294,6 +297,12 @@ IklStatus run(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void
     p.ex_world = ex->world;
     p.ex_rank = ex->rank;
     for (int r = 0; r < ex->world; ++r) p.ex_peer[r] = reinterpret_cast<ExchangeBuf*>(ex->peers[r]);
+  }
+  p.close_epoch = close_epoch ? 1 : 0;
+  if (dual) {
+    p.dual_lam_in = dual->lam_in;
+    p.dual_lam_out = dual->lam_out;
+    p.dual_lr = dual->multiplier_lr;
   }
 
   const int forced = forced_layout();
@@ -360,6 +369,20 @@ IklStatus ikl_lagrangian_forward_backward_allreduce(const IklSpec* spec, const I
                                                     int64_t dtheta_sb, int64_t dtheta_sj, const IklExchange* ex, void* stream) {
   if (!ex) return IKL_ERR_INVALID_ARGUMENT;
   return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream, ex);
+}
+
+IklStatus ikl_lagrangian_forward_dual_step(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* viol_out,
+                                           float* loss_out, double* viol_accum, const IklExchange* ex, const IklDualStep* dual,
+                                           void* stream) {
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, nullptr, 0, 0, false, stream, ex, true, true, dual);
+}
+
+IklStatus ikl_lagrangian_forward_backward_dual_step(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace,
+                                                    float* viol_out, float* loss_out, double* viol_accum, float* dtheta,
+                                                    int64_t dtheta_sb, int64_t dtheta_sj, const IklExchange* ex, const IklDualStep* dual,
+                                                    void* stream) {
+  return run(spec, in, w, workspace, viol_out, loss_out, viol_accum, nullptr, nullptr, dtheta, dtheta_sb, dtheta_sj, true, stream, ex,
+             true, true, dual);
 }
 
 IklStatus ikl_lagrangian_backward(const IklSpec* spec, const IklBatch* in, const IklWeights* w, void* workspace, float* dtheta,

@@ -95,6 +95,12 @@ struct LagrangianParams {
   // in-kernel all-reduce of the K sums over peer memory (ex_world <= 1: off)
   int ex_world, ex_rank;
   ExchangeBuf* ex_peer[kMaxRanks];
+  // epoch-closing launch of a dual step (ikl_lagrangian_*_dual_step): what is exchanged is viol_accum's LOCAL running sum plus
+  // this launch's sums; viol_accum receives the GLOBAL epoch sums and, with dual_lam_out, the multipliers are updated
+  int close_epoch;
+  float dual_lr;
+  const float* dual_lam_in;
+  float* dual_lam_out;
 };
 static_assert(sizeof(LagrangianParams) <= 4096, "kernel parameter block too large");
 
@@ -243,12 +249,32 @@ __device__ __forceinline__ void block_finalize(const LagrangianParams& p, double
 #pragma unroll
     for (int part = 0; part < kFinalParts; ++part) tot += s_fin[part][tid];
   }
-  if (p.ex_world > 1) tot = exchange_sums<K>(p, tot);       // block-uniform branch; contains block barriers
-  if (tid < K) {
-    p.viol_out[tid] = (float)tot;
-    if (p.viol_accum) p.viol_accum[tid] += tot;
-    const float wi = (p.w_dev != nullptr) ? p.w_dev[tid] : p.u.w[tid];
-    s_fin[0][tid] = tot * (double)wi;
+  if (p.close_epoch) {
+    // Last launch of a dual step (scripts/trainer.py:267-286): this launch's sums join the rank's running sum, the running
+    // sums -- not the per-launch ones -- cross NVLink once per epoch, and the dual ascent is applied here, by the block that
+    // holds the global sums: compute, collective and multiplier update in one kernel.  viol_out / loss_out stay this
+    // launch's LOCAL values (with the multipliers of BEFORE the update, as process_batch computes them).
+    double run = tid < K ? tot + p.viol_accum[tid] : 0.0;
+    if (p.ex_world > 1) run = exchange_sums<K>(p, run);     // block-uniform branch; contains block barriers
+    if (tid < K) {
+      const float wi = (p.w_dev != nullptr) ? p.w_dev[tid] : p.u.w[tid];     // read before lam_out (which may alias w_dev) is written
+      p.viol_accum[tid] = run;
+      p.viol_out[tid] = (float)tot;
+      s_fin[0][tid] = tot * (double)wi;
+      if (p.dual_lam_out) {
+        // the arithmetic of dual_update_kernel (trainer.py:280-284): fp32 lam + lr * sum, clamp(min=0); NaN propagates
+        const float next = __fadd_rn(p.dual_lam_in[tid], __fmul_rn(p.dual_lr, (float)run));
+        p.dual_lam_out[tid] = next < 0.f ? 0.f : next;
+      }
+    }
+  } else {
+    if (p.ex_world > 1) tot = exchange_sums<K>(p, tot);       // block-uniform branch; contains block barriers
+    if (tid < K) {
+      p.viol_out[tid] = (float)tot;
+      if (p.viol_accum) p.viol_accum[tid] += tot;
+      const float wi = (p.w_dev != nullptr) ? p.w_dev[tid] : p.u.w[tid];
+      s_fin[0][tid] = tot * (double)wi;
+    }
   }
   __syncthreads();
   if (tid == 0) {

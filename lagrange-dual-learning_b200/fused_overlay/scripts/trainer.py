@@ -140,6 +140,16 @@ class IkLagrangeDualTrainer(object):
     if self.world > 1 and self.device.type == "cuda" and os.environ.get("IKL_PEER_ALLREDUCE", "1") != "0":
       from ikl.exchange import PeerAllReduce
       self._peer_allreduce = PeerAllReduce(sum(p.numel() for p in self.model.parameters()), device=self.device)
+    # The dual step closes inside its last forward launch (fused.DualStep: running sums exchanged over NVLink peer memory
+    # once per epoch + the lambda update, one kernel); IKL_FUSED_DUAL_STEP=0 keeps the separate all-reduce + ikl_dual_update.
+    self._fused_dual_step = self.device.type == "cuda" and os.environ.get("IKL_FUSED_DUAL_STEP", "1") != "0"
+    self._peer_exchange = None
+    if self._fused_dual_step and self.world > 1:
+      if os.environ.get("IKL_PEER_ALLREDUCE", "1") != "0":
+        from ikl.exchange import PeerExchange
+        self._peer_exchange = PeerExchange(device=self.device)
+      else:
+        self._fused_dual_step = False
     if self.use_graph and self.world > 1 and self._peer_allreduce is None and os.environ.get("IKL_GRAPH_DISTRIBUTED", "0") != "1":
       # Capturing the flat NCCL all-reduce of the gradients inside the step graph is implemented (ikl/graph_step.py) but hung
       # on the two-GPU box of this pool (profiles/r02/pytest_multi_graph_hang.log): with NCCL as the exchange the graph is
@@ -354,14 +364,26 @@ class IkLagrangeDualTrainer(object):
       else:
         total = torch.zeros(K, dtype=torch.float64, device=self.device)
         host_lam = self._host_multipliers(lamda)
-        for inputs in self.val_loader:
+        # the epoch's LAST batch closes the dual step inside its own launch: the rank's running sums cross NVLink once, the
+        # block that holds the global sums moves lambda (every rank sees the same number of batches: ShardedBatchSampler)
+        close = fused.DualStep(lamda, self.opt.multiplier_lr, exchange=self._peer_exchange) if self._fused_dual_step else None
+        batches = iter(self.val_loader)
+        upcoming = next(batches, None)
+        closed = False
+        while upcoming is not None:
+          inputs, upcoming = upcoming, next(batches, None)
           for key in inputs:
             inputs[key] = inputs[key].to(self.device, non_blocking=True)
           planes_in = inputs["q_ee_desired"].shape[0] > 1 and inputs["q_ee_desired"].stride(0) == 1
           # train mode (dropout on), as in the reference
           theta = self.model.forward_planes(inputs["input_tensor"]) if planes_in else self.model(inputs["input_tensor"])
+          last = upcoming is None and close is not None
           fused.lagrangian_forward(self.spec, theta, inputs["q_ee_desired"],
-                                   inputs["dynamic_obstacles"] if self.spec.dynamic else None, host_lam, viol_accum=total)
+                                   inputs["dynamic_obstacles"] if self.spec.dynamic else None, host_lam, viol_accum=total,
+                                   close_epoch=close if last else None)
+          closed = closed or last
+        if closed:
+          return close.lam_out
       ikl_dist.all_reduce_sum(total)
       return fused.dual_update(lamda, total, self.opt.multiplier_lr)
 

@@ -16,7 +16,7 @@ MAX_LINKS = 3
 MAX_OBSTACLES = 4
 MAX_CONSTRAINTS = 1 + MAX_LINKS + MAX_LINKS * MAX_OBSTACLES
 MAX_RANKS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 IKL_OK, IKL_ERR_INVALID_ARGUMENT, IKL_ERR_UNSUPPORTED, IKL_ERR_CUDA = 0, 1, 2, 3
 
@@ -47,6 +47,10 @@ class IklExchange(ctypes.Structure):
   _fields_ = [("rank", _c_i32), ("world", _c_i32), ("peers", _c_vp * MAX_RANKS)]
 
 
+class IklDualStep(ctypes.Structure):
+  _fields_ = [("lam_in", _c_vp), ("lam_out", _c_vp), ("multiplier_lr", _c_f)]
+
+
 # name -> (restype, argtypes); mirrors include/ikl.h one to one (tests/test_cabi_symbols.py parses the header)
 _SIGNATURES = {
     "ikl_num_constraints": (_c_i32, [ctypes.POINTER(IklSpec)]),
@@ -61,6 +65,13 @@ _SIGNATURES = {
     "ikl_lagrangian_forward_backward_allreduce": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch),
                                                                  ctypes.POINTER(IklWeights), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                                  _c_i64, ctypes.POINTER(IklExchange), _c_vp]),
+    "ikl_lagrangian_forward_dual_step": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),
+                                                        _c_vp, _c_vp, _c_vp, _c_vp, ctypes.POINTER(IklExchange),
+                                                        ctypes.POINTER(IklDualStep), _c_vp]),
+    "ikl_lagrangian_forward_backward_dual_step": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch),
+                                                                 ctypes.POINTER(IklWeights), _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                                                 _c_i64, ctypes.POINTER(IklExchange), ctypes.POINTER(IklDualStep),
+                                                                 _c_vp]),
     "ikl_allreduce_bytes": (ctypes.c_size_t, [_c_i64, _c_i32]),
     "ikl_allreduce_sum_f32": (ctypes.c_int, [_c_vp, _c_i64, ctypes.POINTER(IklExchange), _c_i64, _c_vp]),
     "ikl_lagrangian_backward": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), ctypes.POINTER(IklWeights),

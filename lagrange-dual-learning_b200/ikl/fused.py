@@ -4,6 +4,8 @@
   lagrangian_forward_backward   the same plus d(loss)/d(theta) in the same pass  (trainer.py:182-247 + :264)
   FusedIkLagrangian             torch.autograd.Function wrapping the two
   dual_update                   lambda <- max(0, lambda + lr * sum)              (trainer.py:280-284)
+  DualStep                      closes a dual step INSIDE the epoch's last forward launch: running sums exchanged over NVLink
+                                peer memory once per epoch + the lambda update, one kernel (trainer.py:267-286)
 
 PyTorch is used for device memory and streams only; all arithmetic happens in libikl.so (sm_100a CUDA),
 reached through the C ABI in include/ikl.h.  There is no CPU fallback: CPU tensors raise.
@@ -100,8 +102,40 @@ def _check_accum(viol_accum, K, device):
   return ctypes.c_void_p(viol_accum.data_ptr())
 
 
+class DualStep(object):
+  """What the launch that closes a dual step needs (include/ikl.h: IklDualStep; scripts/trainer.py:267-286).
+
+  Pass as ``close_epoch=`` to the LAST lagrangian_forward / lagrangian_forward_backward of the epoch, together with the
+  ``viol_accum`` the earlier batches added into.  That one launch adds its sums to the rank's running sum, exchanges the K
+  running sums over NVLink peer memory (``exchange``: ikl.exchange.PeerExchange; None in a single process), leaves the GLOBAL
+  epoch sums in ``viol_accum`` and writes ``lam_out = clamp(lam + multiplier_lr * sum, min=0)`` -- bit-identical on every rank
+  and to `dual_update` on the same sums.  ``lam``: (K,) float32 CUDA tensor (not modified unless ``out`` is it); ``lam=None``
+  only closes the epoch's sum.  The launch's own viol / loss outputs stay LOCAL to the shard."""
+
+  def __init__(self, lam=None, multiplier_lr=0.0, out=None, exchange=None):
+    self.exchange = exchange
+    self.c = None
+    self.lam_out = None
+    if lam is not None:
+      self.lam_in = _require_cuda_f32(lam, "lam").contiguous()
+      if out is None:
+        out = torch.empty_like(self.lam_in)
+      else:
+        _require_cuda_f32(out, "out")
+        if not out.is_contiguous() or out.numel() != self.lam_in.numel() or out.device != self.lam_in.device:
+          raise ValueError("out must be a contiguous tensor like lam")
+      self.lam_out = out
+      self.c = _cabi.IklDualStep()
+      self.c.lam_in, self.c.lam_out, self.c.multiplier_lr = self.lam_in.data_ptr(), out.data_ptr(), float(multiplier_lr)
+
+  def _args(self, K, device):
+    if self.c is not None and (self.lam_in.numel() != K or self.lam_in.device != device):
+      raise ValueError("lam must hold the configuration's %d multipliers on %s" % (K, device))
+    return (self.exchange.byref() if self.exchange is not None else None, ctypes.byref(self.c) if self.c is not None else None)
+
+
 def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, want_q_ee=False,
-                       want_err_sq=False, exchange=None):
+                       want_err_sq=False, exchange=None, close_epoch=None):
   """Constraint sums and Lagrangian of one batch, forward only.
 
   Returns a dict with the reference's output keys: constraint_violations (K,), lagrange_loss (),
@@ -109,6 +143,7 @@ def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol
   ``viol_accum`` (K float64 on device) is incremented by the sums: the running total update_multipliers needs.
   ``exchange`` (ikl.exchange.PeerExchange): this call is one rank's shard; the sums are all-reduced inside the kernel over
   NVLink peer memory and every output holds the GLOBAL value (side outputs are not available in that mode).
+  ``close_epoch`` (DualStep): this is the last batch of a dual step -- see DualStep; needs ``viol_accum``.
   """
   lib = _cabi.load()
   K = spec.num_constraints
@@ -120,7 +155,17 @@ def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol
     B = theta.shape[0]
     q_ee = torch.empty(B, 3, dtype=torch.float32, device=dev) if want_q_ee else None
     err = torch.empty(B, 2, dtype=torch.float32, device=dev) if want_err_sq else None
-    if exchange is not None:
+    if close_epoch is not None:
+      if exchange is not None or want_q_ee or want_err_sq:
+        raise ValueError("close_epoch= carries its own exchange and has no side outputs")
+      if viol_accum is None:
+        raise ValueError("close_epoch= needs the viol_accum the epoch's earlier batches added into")
+      ex_ref, dual_ref = close_epoch._args(K, dev)
+      st = lib.ikl_lagrangian_forward_dual_step(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
+                                                ctypes.c_void_p(_workspace(dev).data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
+                                                ex_ref, dual_ref, _stream_ptr(dev))
+    elif exchange is not None:
       if want_q_ee or want_err_sq:
         raise ValueError("side outputs are per-shard; request them from a call without exchange=")
       st = lib.ikl_lagrangian_forward_allreduce(ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c),
@@ -143,10 +188,11 @@ def lagrangian_forward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol
 
 
 def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=None, viol_accum=None, dtheta=None, exchange=None,
-                                out=None):
+                                out=None, close_epoch=None):
   """One pass: (constraint_violations (K,), lagrange_loss (), dtheta (B,J)) with dtheta = d(sum_i lam_i g_i)/d(theta).
   With ``exchange`` (ikl.exchange.PeerExchange) the call is one rank's shard and the sums / loss are the GLOBAL ones,
-  all-reduced inside the kernel over NVLink peer memory.  ``out``: optional (K+1,) float32 buffer for [sums | loss]."""
+  all-reduced inside the kernel over NVLink peer memory.  ``out``: optional (K+1,) float32 buffer for [sums | loss].
+  ``close_epoch`` (DualStep): this launch closes a dual step -- see DualStep; needs ``viol_accum``; sums / loss stay local."""
   lib = _cabi.load()
   K = spec.num_constraints
   if lam is None:
@@ -170,7 +216,13 @@ def lagrangian_forward_backward(spec, theta, q_ee_desired, obstacles=None, lam=N
     args = (ctypes.byref(spec.c_struct), ctypes.byref(desc), ctypes.byref(w.c), ctypes.c_void_p(_workspace(dev).data_ptr()),
             ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(out.data_ptr() + 4 * K), _check_accum(viol_accum, K, dev),
             ctypes.c_void_p(dtheta.data_ptr()), dtheta.stride(0), dtheta.stride(1))
-    if exchange is not None:
+    if close_epoch is not None:
+      if exchange is not None:
+        raise ValueError("close_epoch= carries its own exchange")
+      if viol_accum is None:
+        raise ValueError("close_epoch= needs the viol_accum the epoch's earlier batches added into")
+      st = lib.ikl_lagrangian_forward_backward_dual_step(*args, *close_epoch._args(K, dev), _stream_ptr(dev))
+    elif exchange is not None:
       st = lib.ikl_lagrangian_forward_backward_allreduce(*args, exchange.byref(), _stream_ptr(dev))
     else:
       st = lib.ikl_lagrangian_forward_backward(*args, _stream_ptr(dev))

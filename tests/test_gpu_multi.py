@@ -129,6 +129,34 @@ def _exchange_worker(rank, world, port, tmpdir):
           assert abs(float(gloss) - want_loss) <= 1e-5 * float((torch.tensor(lam, dtype=torch.float64, device=dev) * scale).sum())
           fwd = fused.lagrangian_forward(spec, args[0], args[1], ob, lam, exchange=ex)
           assert torch.equal(fwd["constraint_violations"], glob), "forward-only and fwd+bwd launches exchange the same sums"
+    # the launch that closes a dual step (fused.DualStep): local running sums, ONE exchange per epoch, lambda moved in the kernel
+    for name in ("cfg_joint_limits_and_4obs_dynamic", "cfg_joint_limits_and_4obs_static", "cfg_joint_limits"):
+      spec = ConstraintSpec.from_config(config_json(name), 3, 0.005, 1.0)
+      K = spec.num_constraints
+      lam = [0.5 + 0.1 * i for i in range(K)]
+      lam_dev = torch.tensor(lam, device=dev)
+      for layout in ("rows", "planes"):
+        for epoch in range(2):                               # interleaves with the per-launch exchange: one shared sequence counter
+          local_total = torch.zeros(K, dtype=torch.float64, device=dev)
+          accum = torch.zeros(K, dtype=torch.float64, device=dev)
+          sizes = (4096 + 512 * rank, 1024, 2048 * (1 - rank))        # the closing batch is EMPTY on rank 1
+          for i, B in enumerate(sizes):
+            theta, q_des, obst = synthetic.make_batch(max(B, 1), seed=50 + 10 * epoch + i + 100 * rank, device=str(dev))
+            theta, q_des, obst = theta[:B], q_des[:B], obst[:B]
+            args = synthetic.to_planes(theta, q_des, obst, max(spec.num_obstacles, 1)) if (layout == "planes" and B > 0) else (theta, q_des, obst)
+            ob = args[2] if spec.dynamic else None
+            fused.lagrangian_forward(spec, args[0], args[1], ob, lam, viol_accum=local_total)
+            close = fused.DualStep(lam_dev, 0.01, exchange=ex) if i == len(sizes) - 1 else None
+            out = fused.lagrangian_forward(spec, args[0], args[1], ob, lam, viol_accum=accum, close_epoch=close)
+          parts = [torch.zeros(K, dtype=torch.float64, device=dev) for _ in range(world)]
+          dist.all_gather(parts, local_total)
+          want = parts[0] + parts[1]                        # the kernel adds the ranks' running sums in rank order, in float64
+          assert torch.equal(accum, want), (name, layout, epoch, rank)
+          assert torch.equal(close.lam_out, fused.dual_update(lam_dev, want, 0.01))
+          lams = [torch.zeros_like(lam_dev) for _ in range(world)]
+          dist.all_gather(lams, close.lam_out)
+          assert torch.equal(lams[0], lams[1]), "lambda must be bit-identical on every rank"
+          fused.lagrangian_forward(spec, args[0], args[1], ob, lam, exchange=ex)       # a per-launch exchange in between
     # CUDA-graph replay: the sequence counter lives on the device, so replays pair up across ranks
     spec = ConstraintSpec.from_config(config_json(NAME), 3, 0.005, 1.0)
     lam = [1.0] * 16

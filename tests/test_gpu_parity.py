@@ -766,6 +766,83 @@ def test_gradient_only_kernels_match_the_full_kernels(name, cuda_device, monkeyp
   grad_close(d_only.cpu().numpy(), dref, truth)
 
 
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_dual_step_closes_inside_the_last_forward_launch(name, cuda_device, monkeypatch):
+  """fused.DualStep (include/ikl.h: ikl_lagrangian_forward[_backward]_dual_step): the epoch's last batch adds its sums to the
+  running sum and moves lambda inside its own launch.  Against the separate path -- plain launches that add into viol_accum,
+  then ikl_dual_update (scripts/trainer.py:267-286) -- the epoch sums, the new lambda, the launch's own sums / Lagrangian and
+  d/dtheta must be bit-identical, in every layout, with host and device multipliers, lam_out aliasing the multipliers the
+  launch reads, an empty closing batch, and against the float64 oracle's dual step."""
+  from ikl import fused, synthetic
+  monkeypatch.delenv("IKL_FORCE_LAYOUT", raising=False)
+  spec, ospec = specs_for(name)
+  dev = cuda_device
+  K = spec.num_constraints
+  lam = (0.25 + 0.1 * np.arange(K)).astype(np.float32)
+  lr = 0.01
+  sizes = (4096, 1000, 2048 + 516)                     # staged tiles, a batch below the staged kernels' threshold, a ragged tail
+  batches = [synthetic.make_batch(B, seed=100 + i) for i, B in enumerate(sizes)]
+  for layout in ("rows", "planes"):
+    dev_batches = []
+    for theta, q_des, obst in batches:
+      th, qd, ob = theta.to(dev), q_des.to(dev), obst.to(dev)
+      a, b_, c = synthetic.to_planes(th, qd, ob, max(spec.num_obstacles, 1)) if layout == "planes" else (th, qd, ob)
+      dev_batches.append((a, b_, c if spec.dynamic else None))
+    for weights in (lam.tolist(), torch.from_numpy(lam).to(dev)):
+      lam_dev = torch.from_numpy(lam).to(dev)
+      # the separate path
+      acc_ref = torch.zeros(K, dtype=torch.float64, device=dev)
+      for a, b_, c in dev_batches:
+        last_ref = fused.lagrangian_forward(spec, a, b_, c, weights, viol_accum=acc_ref)
+      lam_ref = fused.dual_update(lam_dev, acc_ref, lr)
+      # forward-only closing launch
+      acc = torch.zeros(K, dtype=torch.float64, device=dev)
+      for a, b_, c in dev_batches[:-1]:
+        fused.lagrangian_forward(spec, a, b_, c, weights, viol_accum=acc)
+      close_ = fused.DualStep(lam_dev, lr)
+      a, b_, c = dev_batches[-1]
+      last = fused.lagrangian_forward(spec, a, b_, c, weights, viol_accum=acc, close_epoch=close_)
+      assert torch.equal(acc, acc_ref), (name, layout)
+      assert torch.equal(close_.lam_out, lam_ref) and torch.equal(lam_dev, torch.from_numpy(lam).to(dev))
+      assert torch.equal(last["constraint_violations"], last_ref["constraint_violations"])
+      assert torch.equal(last["lagrange_loss"], last_ref["lagrange_loss"])
+      # fwd+bwd closing launch, lam_out aliasing the multipliers the launch itself reads from device memory
+      acc2 = torch.zeros(K, dtype=torch.float64, device=dev)
+      for a, b_, c in dev_batches[:-1]:
+        fused.lagrangian_forward_backward(spec, a, b_, c, weights, viol_accum=acc2)
+      a, b_, c = dev_batches[-1]
+      v_ref, l_ref, d_ref = fused.lagrangian_forward_backward(spec, a, b_, c, weights)
+      w_alias = lam_dev.clone()
+      use = w_alias if isinstance(weights, torch.Tensor) else weights
+      close2 = fused.DualStep(w_alias, lr, out=w_alias)
+      v, l, d = fused.lagrangian_forward_backward(spec, a, b_, c, use, viol_accum=acc2, close_epoch=close2)
+      assert torch.equal(acc2, acc_ref) and torch.equal(w_alias, lam_ref)
+      assert torch.equal(v, v_ref) and torch.equal(l, l_ref) and torch.equal(d, d_ref)
+    # closing without a multiplier update: only the epoch sum
+    acc3 = torch.zeros(K, dtype=torch.float64, device=dev)
+    for i, (a, b_, c) in enumerate(dev_batches):
+      fused.lagrangian_forward(spec, a, b_, c, lam.tolist(), viol_accum=acc3, close_epoch=fused.DualStep() if i == len(dev_batches) - 1 else None)
+    assert torch.equal(acc3, acc_ref)
+    # an empty closing batch (a rank's share of a ragged last batch may be empty): the epoch still closes
+    acc4 = acc_ref.clone()
+    a, b_, c = dev_batches[0]
+    close4 = fused.DualStep(lam_dev, lr)
+    fused.lagrangian_forward(spec, a[:0], b_[:0], c[:0] if c is not None else None, lam.tolist(), viol_accum=acc4, close_epoch=close4)
+    assert torch.equal(acc4, acc_ref) and torch.equal(close4.lam_out, lam_ref)
+  with pytest.raises(ValueError):
+    fused.lagrangian_forward(spec, *dev_batches[0], lam.tolist(), close_epoch=fused.DualStep(lam_dev, lr))
+  # the oracle's dual step on the same three batches
+  total = np.zeros(K)
+  scale = np.zeros(K)
+  for theta, q_des, obst in batches:
+    sums, abs_sums, _, _, _ = oracle_truth(ospec, theta, q_des, obst, lam)
+    total += sums
+    scale += abs_sums
+  assert np.all(np.abs(acc_ref.cpu().numpy() - total) <= 1e-5 * np.maximum(scale, 1e-30))
+  want = np.maximum(0.0, lam.astype(np.float64) + lr * total)
+  close(lam_ref.cpu().numpy(), want, scale=float(np.abs(want).max()))
+
+
 def test_autograd_function_and_general_upstream_gradients(cuda_device):
   from ikl import fused, synthetic
   spec, ospec = specs_for("cfg_joint_limits_and_4obs_dynamic")
