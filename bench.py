@@ -261,6 +261,25 @@ def cpu_baseline_leg(args):
                     "batch of the same workload, mean of 5 after 1 warm-up (%.0f ms each)" % (args.cpu_batch_log2, dtc * 1e3)}
 
 
+def workload_config(args, world, exchange_mode):
+  """The `config` of the bench line -- the workload, identical in both arms (`--impl reference` times a bounded sample of it on
+  the host cores and says which in cpu_baseline.sample).  exchange_mode: "epoch" | "peer" | "nccl" (N > 1 only)."""
+  B = 1 << args.batch_log2
+  epoch = exchange_mode == "epoch"
+  return {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
+          "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
+          "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
+          "step": ("one batch of a dual step (scripts/trainer.py:267-286): fused fwd+bwd launch, 16 sums added to the rank's float64 running "
+                   "sum; the region's LAST launch closes the epoch in the same kernel (exchange of the running sums + lambda update)"
+                   if epoch else "fused fwd+bwd launch with the 16 sums all-reduced every step"),
+          "parallelism": ("single GPU" if world == 1 else
+                          "batch shard per GPU; running sums exchanged ONCE per dual step, inside the closing launch, over NVLink peer "
+                          "memory (ikl_lagrangian_forward_backward_dual_step); no other collective in the timed region" if epoch else
+                          "batch shard per GPU; the 16 violation sums all-reduced inside the fused kernel over NVLink peer memory, every step"
+                          if exchange_mode == "peer" else
+                          "batch shard per GPU; asynchronous NCCL all-reduce of the 16 violation sums per step (overlaps the next step's kernel)")}
+
+
 def run_reference(args):
   """--impl reference: the reference's CPU path (PyTorch eager forward + autograd backward, fp32, all host threads),
   exactly K timed steps after W warm-ups; the per-step sample is sized so that the run stays within minutes.  With
@@ -287,13 +306,70 @@ def run_reference(args):
       "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
       "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
-      "config": {"workload": "three_link_arm + %s, K=16: FK+penalty+Lagrangian fwd+bwd, synthetic theta/target/obstacle batches" % CONFIG_NAME,
-                 "batch_per_step": B, "device": "cpu", "note": "bounded sample of the 2^24-per-GPU workload of the ours arm"},
+      # the workload is the ours arm's, word for word; what this arm actually ran of it is in reference_sample / cpu_baseline.sample
+      "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), args.exchange),
+      "reference_sample": {"batch_per_step": B, "device": "cpu", "layout": "rows (the reference's own tensors)",
+                           "note": "bounded sample of the workload in `config`: same generator, same config file, same slopes and multipliers"},
       "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
       "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
   print(json.dumps(line))
+
+
+def reference_trainer_over_dropins(theta, q_des, obst, lam_dev, dev, batch_log2=22):
+  """process_batch (scripts/trainer.py:159-249) + lagrange_loss.backward() of the reference's own trainer class, unmodified,
+  on the GPU over the function-level drop-ins (one libikl.so launch per FK / penalty call, forward and backward), theta as
+  a leaf.  The same harness as tests/test_gpu_reference_trainer.py."""
+  import tempfile
+  import torch
+  from ikl import _cabi
+  from baseline import ref_harness as H
+  if not H.have_reference_tree():
+    return {"unavailable": "baseline/_ref is not installed"}
+  trainer_mod, options_mod = H.load_reference_scripts()
+  H.assert_resolution(trainer_mod)
+  tmp = tempfile.mkdtemp(prefix="ikl_bench_dropin_")
+  cfg_path = os.path.join(H.REF_TREE, "resources", CONFIG_NAME + ".json")
+  opt = H.reference_options(options_mod, ["--model_name", "bench", "--config_file", cfg_path, "--log_dir", tmp, "--num_workers", "0",
+                                          "--train_dataset_size", "16", "--val_dataset_size", "16", "--batch_size", "16",
+                                          "--penalty_good_slope", str(GOOD_SLOPE), "--penalty_bad_slope", str(BAD_SLOPE), "--hidden_units", "16"])
+  import contextlib
+  with H.git_worktree(tmp), contextlib.redirect_stdout(sys.stderr):
+    tr = trainer_mod.IkLagrangeDualTrainer(opt)
+  Bd = 1 << batch_log2
+
+  class FixedTheta(torch.nn.Module):
+    def __init__(self, t):
+      super().__init__()
+      self.theta = torch.nn.Parameter(t.clone())
+
+    def forward(self, x):
+      return self.theta
+  tr.model = FixedTheta(theta[:Bd]).to(dev)
+  inputs = {"input_tensor": torch.zeros(Bd, 20, device=dev), "q_ee_desired": q_des[:Bd].clone(), "joint_theta": theta[:Bd].clone(),
+            "dynamic_obstacles": obst[:Bd].clone()}
+
+  def step():
+    out = tr.process_batch(dict(inputs), lam_dev)
+    tr.model.zero_grad()
+    out["lagrange_loss"].backward()
+  step()
+  torch.cuda.synchronize()
+  n0 = _cabi.launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(3):
+    step()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / 3
+  res = {"samples_per_s": Bd / (ms * 1e-3), "ms_per_step": ms, "batch": Bd, "libikl_launches_per_step": (_cabi.launch_count() - n0) // 3,
+         "note": "the reference's own IkLagrangeDualTrainer.process_batch + backward(), file baseline/_ref/scripts/trainer.py unmodified, FK and "
+                 "every penalty call one CUDA drop-in launch each way; the rest is the trainer's own torch glue (slice-assign, sums)"}
+  del tr, inputs
+  torch.cuda.empty_cache()
+  return res
 
 
 def multi_gpu_check(args, spec, dev, world, rank, lam, exchange):
@@ -811,17 +887,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "three_link_arm + %s, K=16: fused FK+penalty+Lagrangian fwd+bwd, batch 2^%d per GPU" % (CONFIG_NAME, args.batch_log2),
-                   "batch_per_gpu": B, "layout": args.layout, "slopes": [GOOD_SLOPE, BAD_SLOPE], "weights": "by value (host lambda)",
-                   "l2": "no flush: each step streams %.2f GB of inputs (> 126 MB L2)" % (B * (100 if args.layout == "rows" else 68) / 1e9),
-                   "step": ("one batch of a dual step (scripts/trainer.py:267-286): fused fwd+bwd launch, 16 sums added to the rank's float64 running "
-                            "sum; the region's LAST launch closes the epoch in the same kernel (exchange of the running sums + lambda update)"
-                            if epoch_mode else "fused fwd+bwd launch with the 16 sums all-reduced every step"),
-                   "parallelism": ("single GPU" if world == 1 else
-                                   "batch shard per GPU; running sums exchanged ONCE per dual step, inside the closing launch, over NVLink peer "
-                                   "memory (ikl_lagrangian_forward_backward_dual_step); no other collective in the timed region" if epoch_mode else
-                                   "batch shard per GPU; the 16 violation sums all-reduced inside the fused kernel over NVLink peer memory, every step" if exchange is not None else
-                                   "batch shard per GPU; asynchronous NCCL all-reduce of the 16 violation sums per step (overlaps the next step's kernel)")},
+        "config": workload_config(args, world, "epoch" if epoch_mode else ("peer" if exchange is not None else "nccl")),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
                      "peak_source": peak_src},
@@ -895,6 +961,13 @@ def run_ours(args):
       torch.cuda.empty_cache()
     except Exception as e:
       extras["reference_eager_cuda"] = {"unavailable": str(e)[:200]}
+
+    # level (i) of the boundary, timed: the reference's UNMODIFIED scripts/trainer.py (baseline/_ref, loaded by file path) with
+    # kinematics.* resolving to this repo's function-level CUDA drop-ins -- what a user gets with zero code changes
+    try:
+      extras["reference_trainer_over_dropins"] = reference_trainer_over_dropins(theta, q_des, obst, lam_dev, dev)
+    except Exception as e:
+      extras["reference_trainer_over_dropins"] = {"unavailable": str(e)[:200]}
 
   # ---- end to end through the host-buffer API (rank-local; every rank does the same work) -------------------
   e2e = None

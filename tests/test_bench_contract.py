@@ -37,6 +37,12 @@ def test_reference_arm_prints_one_contract_line(kind):
   assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
   assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
   assert "workload" in d["config"] and d["gpu_launches"] == 0 and d["value"] > 0
+  # the config is the ours arm's, word for word (same function); what this arm sampled of it is stated beside it
+  sys.path.insert(0, ROOT)
+  import argparse
+  import bench
+  want = bench.workload_config(argparse.Namespace(batch_log2=24, layout="planes"), 1, "epoch")
+  assert d["config"] == want and d["reference_sample"]["batch_per_step"] == 1 << 12 and d["reference_sample"]["device"] == "cpu"
 
 
 def test_reference_arm_other_ranks_exit_quietly():
