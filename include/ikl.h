@@ -240,12 +240,14 @@ IklStatus ikl_circle_penalty_forward(const float* jx, int64_t s_jx, const float*
                                      const float* radius, int64_t s_r, int64_t n,
                                      float inside_slope, float outside_slope, float* out, void* stream);
 
-/* Backward: grad_out (n, contiguous) -> d/djx, d/djy (n, contiguous; either may be NULL), and optionally
- * d/dox, d/doy, d/dradius per element (caller reduces over broadcast dims). */
+/* Backward: grad_out (n elements, element stride s_g; s_g = 0: ONE value for every element, which is what the
+ * `.sum()` the reference applies to every penalty hands back -- scripts/trainer.py:204, :239 -- so the expanded gradient
+ * is never materialised) -> d/djx, d/djy (n, contiguous; either may be NULL), and optionally d/dox, d/doy, d/dradius
+ * per element (caller reduces over broadcast dims). */
 IklStatus ikl_circle_penalty_backward(const float* jx, int64_t s_jx, const float* jy, int64_t s_jy,
                                       const float* ox, int64_t s_ox, const float* oy, int64_t s_oy,
                                       const float* radius, int64_t s_r, int64_t n,
-                                      float inside_slope, float outside_slope, const float* grad_out,
+                                      float inside_slope, float outside_slope, const float* grad_out, int64_t s_g,
                                       float* d_jx, float* d_jy, float* d_ox, float* d_oy, float* d_radius,
                                       void* stream);
 
@@ -256,7 +258,7 @@ IklStatus ikl_joint_limit_penalty_forward(const float* theta, int64_t s_t, const
 
 IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, const float* lo, int64_t s_lo,
                                            const float* hi, int64_t s_hi, int64_t n,
-                                           float inside_slope, float outside_slope, const float* grad_out,
+                                           float inside_slope, float outside_slope, const float* grad_out, int64_t s_g,
                                            float* d_theta, float* d_lo, float* d_hi, void* stream);
 
 /* ---- the callers either side of the path, on the device ------------------------------------------ */

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kEwThreads) circle_backward_kernel(const float
                                                                     long long s_jy, const float* __restrict__ ox, long long s_ox,
                                                                     const float* __restrict__ oy, long long s_oy,
                                                                     const float* __restrict__ rad, long long s_r, long long n, float a_in,
-                                                                    float a_out, const float* __restrict__ gout, float* __restrict__ d_jx,
+                                                                    float a_out, const float* __restrict__ gout, long long s_g, float* __restrict__ d_jx,
                                                                     float* __restrict__ d_jy, float* __restrict__ d_ox,
                                                                     float* __restrict__ d_oy, float* __restrict__ d_r) {
   const long long step = (long long)gridDim.x * kEwThreads;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kEwThreads) circle_backward_kernel(const float
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long i = i0 + u * step;
-      if (i < n) { a[u] = jx[i * s_jx]; b[u] = jy[i * s_jy]; c[u] = ox[i * s_ox]; e[u] = oy[i * s_oy]; r[u] = rad[i * s_r]; go[u] = gout[i]; }
+      if (i < n) { a[u] = jx[i * s_jx]; b[u] = jy[i * s_jy]; c[u] = ox[i * s_ox]; e[u] = oy[i * s_oy]; r[u] = rad[i * s_r]; go[u] = gout[i * s_g]; }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f 
 
 __global__ void __launch_bounds__(kEwThreads) jl_backward_kernel(const float* __restrict__ th, long long s_t, const float* __restrict__ lo,
                                                                 long long s_lo, const float* __restrict__ hi, long long s_hi, long long n,
-                                                                float a_in, float a_out, const float* __restrict__ gout,
+                                                                float a_in, float a_out, const float* __restrict__ gout, long long s_g,
                                                                 float* __restrict__ d_th, float* __restrict__ d_lo, float* __restrict__ d_hi) {
   const float h_in = a_in * 0.5f, h_out = a_out * 0.5f;
   const long long step = (long long)gridDim.x * kEwThreads;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kEwThreads) jl_backward_kernel(const float* __
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long i = i0 + u * step;
-      if (i < n) { l[u] = lo[i * s_lo]; h[u] = hi[i * s_hi]; t[u] = th[i * s_t]; go[u] = gout[i]; }
+      if (i < n) { l[u] = lo[i * s_lo]; h[u] = hi[i * s_hi]; t[u] = th[i * s_t]; go[u] = gout[i * s_g]; }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
@@ -286,14 +286,14 @@ IklStatus ikl_circle_penalty_forward(const float* jx, int64_t s_jx, const float*
 
 IklStatus ikl_circle_penalty_backward(const float* jx, int64_t s_jx, const float* jy, int64_t s_jy, const float* ox, int64_t s_ox,
                                       const float* oy, int64_t s_oy, const float* radius, int64_t s_r, int64_t n, float inside_slope,
-                                      float outside_slope, const float* grad_out, float* d_jx, float* d_jy, float* d_ox, float* d_oy,
-                                      float* d_radius, void* stream) {
+                                      float outside_slope, const float* grad_out, int64_t s_g, float* d_jx, float* d_jy, float* d_ox,
+                                      float* d_oy, float* d_radius, void* stream) {
   if (n < 0 || !(inside_slope >= 0.f) || !(outside_slope >= 0.f)) return IKL_ERR_INVALID_ARGUMENT;
   if (n == 0) return IKL_OK;
   if (!jx || !jy || !ox || !oy || !radius || !grad_out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
   circle_backward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(jx, s_jx, jy, s_jy, ox, s_ox, oy, s_oy, radius, s_r, n,
-                                                                               inside_slope, outside_slope, grad_out, d_jx, d_jy, d_ox,
+                                                                               inside_slope, outside_slope, grad_out, s_g, d_jx, d_jy, d_ox,
                                                                                d_oy, d_radius);
   return cuda_status(cudaGetLastError());
 }
@@ -309,14 +309,14 @@ IklStatus ikl_joint_limit_penalty_forward(const float* theta, int64_t s_t, const
 }
 
 IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, const float* lo, int64_t s_lo, const float* hi, int64_t s_hi,
-                                           int64_t n, float inside_slope, float outside_slope, const float* grad_out, float* d_theta,
-                                           float* d_lo, float* d_hi, void* stream) {
+                                           int64_t n, float inside_slope, float outside_slope, const float* grad_out, int64_t s_g,
+                                           float* d_theta, float* d_lo, float* d_hi, void* stream) {
   if (n < 0 || !(inside_slope >= 0.f) || !(outside_slope >= 0.f)) return IKL_ERR_INVALID_ARGUMENT;
   if (n == 0) return IKL_OK;
   if (!theta || !lo || !hi || !grad_out) return IKL_ERR_INVALID_ARGUMENT;
   count_launch();
   jl_backward_kernel<<<ew_grid_unrolled(n), kEwThreads, 0, (cudaStream_t)stream>>>(theta, s_t, lo, s_lo, hi, s_hi, n, inside_slope, outside_slope,
-                                                                           grad_out, d_theta, d_lo, d_hi);
+                                                                           grad_out, s_g, d_theta, d_lo, d_hi);
   return cuda_status(cudaGetLastError());
 }
 

@@ -80,9 +80,9 @@ _SIGNATURES = {
     "ikl_fk_forward": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i32, ctypes.POINTER(_c_f), _c_vp, _c_vp]),
     "ikl_fk_backward": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i32, ctypes.POINTER(_c_f), _c_vp, _c_vp, _c_vp]),
     "ikl_circle_penalty_forward": (ctypes.c_int, [_c_vp, _c_i64] * 5 + [_c_i64, _c_f, _c_f, _c_vp, _c_vp]),
-    "ikl_circle_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 5 + [_c_i64, _c_f, _c_f, _c_vp] + [_c_vp] * 5 + [_c_vp]),
+    "ikl_circle_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 5 + [_c_i64, _c_f, _c_f, _c_vp, _c_i64] + [_c_vp] * 5 + [_c_vp]),
     "ikl_joint_limit_penalty_forward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp, _c_vp]),
-    "ikl_joint_limit_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp] + [_c_vp] * 3 + [_c_vp]),
+    "ikl_joint_limit_penalty_backward": (ctypes.c_int, [_c_vp, _c_i64] * 3 + [_c_i64, _c_f, _c_f, _c_vp, _c_i64] + [_c_vp] * 3 + [_c_vp]),
     "ikl_dataset_generate": (ctypes.c_int, [ctypes.POINTER(IklSpec), _c_i64, ctypes.c_uint64, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "ikl_eval_stats": (ctypes.c_int, [ctypes.POINTER(IklSpec), ctypes.POINTER(IklBatch), _c_f, _c_vp, _c_vp, _c_vp]),
     "ikl_set_reserved_sms": (None, [_c_i32]),

@@ -38,6 +38,24 @@ def _stream(dev):
   return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+class _on_device(object):
+  """`with torch.cuda.device(dev)` only when dev is not already current: an unchanged scripts/trainer.py makes ~30 of these
+  calls per step and is host-bound, so the common case must not pay for a device switch that does nothing."""
+  __slots__ = ("guard",)
+
+  def __init__(self, dev):
+    self.guard = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+  def __enter__(self):
+    if self.guard is not None:
+      self.guard.__enter__()
+
+  def __exit__(self, *exc):
+    if self.guard is not None:
+      return self.guard.__exit__(*exc)
+    return False
+
+
 def _vp(t):
   return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -54,7 +72,7 @@ class _ForwardKinematics(torch.autograd.Function):
     lib = _cabi.load()
     B, J = theta.shape
     tips = torch.empty(J, B, 3, dtype=torch.float32, device=theta.device)
-    with torch.cuda.device(theta.device):
+    with _on_device(theta.device):
       st = lib.ikl_fk_forward(_vp(theta), theta.stride(0), theta.stride(1), B, J, _lengths(link_lengths, J), _vp(tips),
                               _stream(theta.device))
     _cabi.check(st, "ikl_fk_forward")
@@ -70,7 +88,7 @@ class _ForwardKinematics(torch.autograd.Function):
     g = torch.stack([torch.zeros(B, 3, dtype=torch.float32, device=theta.device) if gk is None else gk.to(torch.float32)
                      for gk in grads]).contiguous()
     dtheta = torch.empty(B, J, dtype=torch.float32, device=theta.device)
-    with torch.cuda.device(theta.device):
+    with _on_device(theta.device):
       st = lib.ikl_fk_backward(_vp(theta), theta.stride(0), theta.stride(1), B, J, _lengths(ctx.link_lengths, J), _vp(g),
                                _vp(dtheta), _stream(theta.device))
     _cabi.check(st, "ikl_fk_backward")
@@ -93,6 +111,8 @@ def fk_forward_kinematics(theta, link_lengths=None):
 # ---- elementwise penalties -----------------------------------------------------------------------------------
 def _flat_view(t, shape):
   """Broadcast t to `shape` and describe it as (tensor_to_keep_alive, data_ptr, element stride) over prod(shape) elements."""
+  if t.dim() == 1 and len(shape) == 1 and t.shape[0] == shape[0]:
+    return t, (t.stride(0) if shape[0] > 1 else 0)          # the trainer's case: a column view or an expand()-ed limit, as is
   e = t.expand(shape)
   n = e.numel()
   if n <= 1 or all(s == 0 for s, d in zip(e.stride(), e.shape) if d > 1):
@@ -106,6 +126,15 @@ def _flat_view(t, shape):
 
 
 def _prep(dev, *ts):
+  # fast path (every call an unchanged scripts/trainer.py makes): float32 tensors already on the device, one shape
+  t0 = ts[0]
+  if isinstance(t0, torch.Tensor):
+    shape = t0.shape
+    for t in ts:
+      if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.device == dev and t.shape == shape):
+        break
+    else:
+      return ts, shape
   out = []
   for i, t in enumerate(ts):
     if not isinstance(t, torch.Tensor):
@@ -125,13 +154,14 @@ class _CirclePenalty(torch.autograd.Function):
   @staticmethod
   def forward(ctx, jx, jy, ox, oy, radius, inside_slope, outside_slope):
     lib = _cabi.load()
-    shape = torch.broadcast_shapes(jx.shape, jy.shape, ox.shape, oy.shape, radius.shape)
+    shape = jx.shape if jx.shape == jy.shape == ox.shape == oy.shape == radius.shape else \
+        torch.broadcast_shapes(jx.shape, jy.shape, ox.shape, oy.shape, radius.shape)
     views = [_flat_view(t, shape) for t in (jx, jy, ox, oy, radius)]
     out = torch.empty(shape, dtype=torch.float32, device=jx.device)
     args = []
     for v, s in views:
       args += [_vp(v), s]
-    with torch.cuda.device(jx.device):
+    with _on_device(jx.device):
       st = lib.ikl_circle_penalty_forward(*args, out.numel(), inside_slope, outside_slope, _vp(out), _stream(jx.device))
     _cabi.check(st, "ikl_circle_penalty_forward")
     ctx.save_for_backward(jx, jy, ox, oy, radius)
@@ -144,14 +174,16 @@ class _CirclePenalty(torch.autograd.Function):
     operands = ctx.saved_tensors
     shape = grad_out.shape
     views = [_flat_view(t, shape) for t in operands]
-    g = grad_out.to(torch.float32).contiguous()
+    # the gradient of the `.sum()` the trainer applies (scripts/trainer.py:239) is ONE value expand()-ed over the batch: it is
+    # handed to the kernel with element stride 0 instead of being materialised
+    g, s_g = _flat_view(grad_out if grad_out.dtype == torch.float32 else grad_out.to(torch.float32), shape)
     need = ctx.needs_input_grad[:5]
     outs = [torch.empty(shape, dtype=torch.float32, device=g.device) if n else None for n in need]
     args = []
     for v, s in views:
       args += [_vp(v), s]
-    with torch.cuda.device(g.device):
-      st = lib.ikl_circle_penalty_backward(*args, g.numel(), ctx.slopes[0], ctx.slopes[1], _vp(g), *[_vp(o) for o in outs],
+    with _on_device(g.device):
+      st = lib.ikl_circle_penalty_backward(*args, grad_out.numel(), ctx.slopes[0], ctx.slopes[1], _vp(g), s_g, *[_vp(o) for o in outs],
                                            _stream(g.device))
     _cabi.check(st, "ikl_circle_penalty_backward")
     grads = [None if o is None else _reduce_to(o, t.shape) for o, t in zip(outs, operands)]
@@ -173,13 +205,13 @@ class _JointLimitPenalty(torch.autograd.Function):
   @staticmethod
   def forward(ctx, theta, lo, hi, inside_slope, outside_slope):
     lib = _cabi.load()
-    shape = torch.broadcast_shapes(theta.shape, lo.shape, hi.shape)
+    shape = theta.shape if theta.shape == lo.shape == hi.shape else torch.broadcast_shapes(theta.shape, lo.shape, hi.shape)
     views = [_flat_view(t, shape) for t in (theta, lo, hi)]
     out = torch.empty(shape, dtype=torch.float32, device=theta.device)
     args = []
     for v, s in views:
       args += [_vp(v), s]
-    with torch.cuda.device(theta.device):
+    with _on_device(theta.device):
       st = lib.ikl_joint_limit_penalty_forward(*args, out.numel(), inside_slope, outside_slope, _vp(out), _stream(theta.device))
     _cabi.check(st, "ikl_joint_limit_penalty_forward")
     ctx.save_for_backward(theta, lo, hi)
@@ -192,14 +224,14 @@ class _JointLimitPenalty(torch.autograd.Function):
     operands = ctx.saved_tensors
     shape = grad_out.shape
     views = [_flat_view(t, shape) for t in operands]
-    g = grad_out.to(torch.float32).contiguous()
+    g, s_g = _flat_view(grad_out if grad_out.dtype == torch.float32 else grad_out.to(torch.float32), shape)   # trainer.py:204: stride 0
     need = ctx.needs_input_grad[:3]
     outs = [torch.empty(shape, dtype=torch.float32, device=g.device) if n else None for n in need]
     args = []
     for v, s in views:
       args += [_vp(v), s]
-    with torch.cuda.device(g.device):
-      st = lib.ikl_joint_limit_penalty_backward(*args, g.numel(), ctx.slopes[0], ctx.slopes[1], _vp(g), *[_vp(o) for o in outs],
+    with _on_device(g.device):
+      st = lib.ikl_joint_limit_penalty_backward(*args, grad_out.numel(), ctx.slopes[0], ctx.slopes[1], _vp(g), s_g, *[_vp(o) for o in outs],
                                                 _stream(g.device))
     _cabi.check(st, "ikl_joint_limit_penalty_backward")
     grads = [None if o is None else _reduce_to(o, t.shape) for o, t in zip(outs, operands)]

@@ -301,6 +301,41 @@ def test_penalty_dropins_accept_trainer_style_views(cuda_device):
   np.testing.assert_allclose(got2.detach().cpu().numpy(), ref2.numpy(), rtol=0, atol=3e-7)
 
 
+def test_penalty_backward_takes_the_expanded_gradient_of_sum_as_is(cuda_device):
+  """`.sum()` hands its backward ONE value expand()-ed over the batch (element stride 0; scripts/trainer.py:204, :239).  The
+  drop-ins pass it to the kernel with that stride instead of materialising it: gradients must equal, bit for bit, those of
+  a materialised gradient tensor of the same values; a strided (every other element) and a 2-D broadcast gradient too."""
+  import kinematics.penalties as pen
+  torch.manual_seed(9)
+  B = 5000
+  q = torch.randn(B, 3, device=cuda_device)
+  ob = torch.rand(B, 4, 4, device=cuda_device)
+  th = (torch.randn(B, 3, device=cuda_device) * 2)
+  lim = torch.tensor([-2.094395, 2.094395], device=cuda_device).unsqueeze(0).expand(B, -1)
+
+  def grads(upstream):
+    qg, thg = q.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    c = pen.piecewise_circle_penalty(qg[:, 0], qg[:, 1], ob[:, 1, 0], ob[:, 1, 1], ob[:, 1, 2], 1.0, 0.005)
+    j = pen.piecewise_joint_limit_penalty(thg[:, 2], lim[:, 0], lim[:, 1], 0.005, 1.0)
+    upstream(c, j)
+    return qg.grad.clone(), thg.grad.clone()
+  g_sum = grads(lambda c, j: (2.5 * c.sum() + 2.5 * j.sum()).backward())                       # expanded scalar: stride 0
+  g_mat = grads(lambda c, j: torch.autograd.backward([c, j], [torch.full((B,), 2.5, device=cuda_device)] * 2))
+  assert torch.equal(g_sum[0], g_mat[0]) and torch.equal(g_sum[1], g_mat[1])
+  w = torch.randn(2 * B, device=cuda_device)
+  g_str = grads(lambda c, j: torch.autograd.backward([c, j], [w[::2], w[::2]]))                 # element stride 2
+  g_con = grads(lambda c, j: torch.autograd.backward([c, j], [w[::2].contiguous(), w[::2].contiguous()]))
+  assert torch.equal(g_str[0], g_con[0]) and torch.equal(g_str[1], g_con[1])
+  qg = q.clone().requires_grad_(True)
+  c2 = pen.piecewise_circle_penalty(qg[:, 0:1], qg[:, 1:2], ob[0, :, 0], ob[0, :, 1], ob[0, :, 2], 1.0, 0.1)   # (B,4)
+  c2.sum().backward()
+  g2 = qg.grad.clone()
+  qg.grad = None
+  c2 = pen.piecewise_circle_penalty(qg[:, 0:1], qg[:, 1:2], ob[0, :, 0], ob[0, :, 1], ob[0, :, 2], 1.0, 0.1)
+  c2.backward(torch.ones(B, 4, device=cuda_device))
+  assert torch.equal(g2, qg.grad)
+
+
 def test_dropins_refuse_dtypes_they_would_have_to_narrow(cuda_device):
   """The reference's functions are dtype-generic (a float64 tensor is evaluated in float64); the CUDA drop-ins compute in
   float32 only and say so instead of narrowing silently."""
