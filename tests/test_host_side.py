@@ -287,3 +287,34 @@ def test_batch_outputs_behaves_like_the_reference_dict():
   assert fresh()["joint_angle_l2"] == 3
   with pytest.raises(KeyError):
     fresh()["missing"]
+
+
+def test_dropin_wrappers_describe_the_trainers_operands_without_copies():
+  """Host logic of ikl/ops.py (no launch): the operands scripts/trainer.py passes -- column views of (B,3) / (B,4,4) tensors,
+  expand()-ed limits, the expanded gradient of `.sum()` -- are handed to the kernels as (pointer, element stride) with no
+  copy; anything else is broadcast (and copied only when it is not expressible as one stride)."""
+  from ikl import ops
+  B = 64
+  q = torch.randn(B, 3)
+  ob = torch.rand(B, 4, 4)
+  lim = torch.Tensor([-2.0, 2.0]).unsqueeze(0).expand(B, -1)
+  shape = torch.Size([B])
+  for t, stride in ((q[:, 1], 3), (ob[:, 2, 0], 16), (lim[:, 0], 0), (torch.ones(()).expand(B), 0), (torch.arange(2.0 * B)[::2], 2)):
+    v, s = ops._flat_view(t, shape)
+    assert s == stride and v.data_ptr() == t.data_ptr(), (t.shape, t.stride(), s)
+  assert ops._flat_view(torch.ones(1), torch.Size([1]))[1] == 0
+  # a scalar against the batch, and a 2-D broadcast that no single stride describes
+  v, s = ops._flat_view(torch.tensor(0.4), shape)
+  assert s == 0
+  v, s = ops._flat_view(q[:, 0:1], torch.Size([B, 4]))
+  assert s == 1 and v.is_contiguous() and v.shape == (B, 4)
+  v, s = ops._flat_view(ob[0, :, 2], torch.Size([B, 4]))
+  assert s == 1 and v.is_contiguous()
+  # _prep: the trainer's call (float32, one device, one shape) passes through untouched; other inputs are converted / refused
+  cpu = torch.device("cpu")
+  same, shp = ops._prep(cpu, q[:, 0], q[:, 1], ob[:, 0, 0])
+  assert shp == shape and [a.data_ptr() for a in same] == [q[:, 0].data_ptr(), q[:, 1].data_ptr(), ob[:, 0, 0].data_ptr()]
+  mixed, shp = ops._prep(cpu, q[:, 0:1], 0.5, ob[0, :, 2])
+  assert shp == (B, 4) and mixed[1].dtype == torch.float32
+  with pytest.raises(TypeError):
+    ops._prep(cpu, q[:, 0], q[:, 1].double())
