@@ -256,6 +256,8 @@ IklStatus ikl_joint_limit_penalty_forward(const float* theta, int64_t s_t, const
                                           const float* hi, int64_t s_hi, int64_t n,
                                           float inside_slope, float outside_slope, float* out, void* stream);
 
+/* grad_out: n elements with element stride s_g (0 = one value for every element: the gradient of `.sum()`,
+ * scripts/trainer.py:204). */
 IklStatus ikl_joint_limit_penalty_backward(const float* theta, int64_t s_t, const float* lo, int64_t s_lo,
                                            const float* hi, int64_t s_hi, int64_t n,
                                            float inside_slope, float outside_slope, const float* grad_out, int64_t s_g,
