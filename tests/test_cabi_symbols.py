@@ -119,3 +119,31 @@ def test_product_tree_never_imports_the_oracle():
         text = open(os.path.join(base, f), errors="ignore").read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(base, f)
         assert "ik_oracle" not in text, os.path.join(base, f)
+
+
+def _kernel_sass(mangled):
+  import shutil
+  import subprocess
+  if shutil.which("cuobjdump") is None:
+    pytest.skip("cuobjdump not on PATH")
+  path = build.build()
+  out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, path], capture_output=True, text=True).stdout
+  assert "Function : " + mangled in out, "kernel %s is not in libikl.so" % mangled
+  return out
+
+
+def test_benchmark_kernels_are_sm100a_tma_and_packed_fp32():
+  """The kernels bench.py times are what DESIGN.md section 3 / 4.1 says they are: sm_100a code whose loads are TMA
+  (tensor-map UTMALDG for planes, bulk UBLKCP for rows) completing on mbarriers (SYNCS), with the per-pair maths on the
+  packed fp32 pipe (FFMA2 / FADD2 / FMUL2) and one MUFU.RSQ per tip-circle term.  No GPU needed: SASS of the built library."""
+  cfg5 = "NS_3CfgILi%dELi3ELi4ELb1ELb1ELi1ELb1EEEEEvNS_16LagrangianParamsE"     # 3 links, 4 dynamic obstacles, limits, fwd+bwd host lambda
+  planes = _kernel_sass("_ZN3ikl28lagrangian_planes_tma_kernelI" + cfg5 % 2)
+  rows = _kernel_sass("_ZN3ikl26lagrangian_rows_tma_kernelI" + cfg5 % 1)
+  for sass in (planes, rows):
+    assert "arch = sm_100a" in sass
+    assert sass.count("FFMA2") > 100 and sass.count("FADD2") > 20 and sass.count("FMUL2") > 20
+    assert sass.count("MUFU.RSQ") >= 24                     # 12 terms x 2 samples (the exact redo adds its own)
+    assert "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+    assert not re.search(r"\b(HMMA|UTCHMMA|IMMA)\b", sass)   # not a contraction: no tensor-core instructions, by design
+  assert "UTMALDG.2D" in planes and "UTMALDG.3D" in planes
+  assert "UBLKCP.S.G" in rows
