@@ -5,10 +5,8 @@ baseline/_ref/ (the byte-for-byte copy tools/install_ref.py makes; it travels to
 from /root/reference -- under private module names, so they cannot be confused with this repo's CUDA drop-ins of the same
 names.  hypothesis draws shapes, slopes (either order, equal, zero), limits (asymmetric, reversed) and inputs, including
 exact kinks; the oracle must reproduce values AND gradients bit for bit in float32 and float64.  CPU only."""
-import importlib.util
 import os
 import sys
-import types
 
 import numpy as np
 import pytest
@@ -20,44 +18,9 @@ from conftest import ROOT
 from oracle import ik_oracle as O
 
 
-def _reference_root():
-  for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
-    if os.path.exists(os.path.join(root, "kinematics", "penalties.py")):
-      return root
-  return None
-
-
-REF_ROOT = _reference_root()
-pytestmark = pytest.mark.skipif(REF_ROOT is None, reason="no copy of the reference (baseline/_ref or /root/reference)")
-
-
-def _load(name, rel):
-  spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
-  mod = importlib.util.module_from_spec(spec)
-  spec.loader.exec_module(mod)
-  return mod
-
-
 @pytest.fixture(scope="module")
-def ref():
-  """(forward_kinematics module, penalties module) of the reference.  forward_kinematics.py:4 imports utils.constants: the
-  reference's own file is supplied for the duration of the import under that name and then removed again."""
-  consts = _load("_ref_utils_constants", os.path.join("utils", "constants.py"))
-  saved = {k: sys.modules.get(k) for k in ("utils", "utils.constants")}
-  pkg = types.ModuleType("utils")
-  pkg.constants = consts
-  sys.modules["utils"], sys.modules["utils.constants"] = pkg, consts
-  try:
-    fk = _load("_ref_forward_kinematics", os.path.join("kinematics", "forward_kinematics.py"))
-  finally:
-    for k, v in saved.items():
-      if v is None:
-        sys.modules.pop(k, None)
-      else:
-        sys.modules[k] = v
-  pen = _load("_ref_penalties", os.path.join("kinematics", "penalties.py"))
-  assert os.path.realpath(fk.__file__).startswith(os.path.realpath(REF_ROOT))
-  return fk, pen
+def ref(live_reference):
+  return live_reference
 
 
 _SETTINGS = dict(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
