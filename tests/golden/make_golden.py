@@ -249,7 +249,10 @@ def golden_dual_trajectory(trainer_mod, options_mod, net_mod, tmp):
     torch.save({"train": ds_dict(tr.train_dataset), "val": ds_dict(tr.val_dataset),
                 "init_state": init_state, "final_state": final_state,
                 "lambda_history": torch.stack(lam_hist), "lambda_isolated_step": lam_iso,
-                "opt": {k: v for k, v in vars(opt).items() if isinstance(v, (int, float, str, bool, type(None)))}},
+                # log_dir is a random temporary directory and the trainer records the work tree's commit (trainer.py:105-107):
+                # both are stored as placeholders so that the file is byte-reproducible
+                "opt": {k: ("<tmp>" if k == "log_dir" else "<head>" if k.startswith("commit_has") else v) for k, v in vars(opt).items()
+                        if isinstance(v, (int, float, str, bool, type(None)))}},
                os.path.join(HERE, "dual_trajectory_%s.pt" % name))
 
 
