@@ -132,3 +132,29 @@ def test_fk_dropin_against_the_live_reference(cuda_device, live_reference):
     # d/dtheta: sums of +-sin / cos of the same float32 angles weighted by |w| <= 1 -- at most 6 terms of ~1.5e-7 each, plus
     # the round-off of the reference's own float32 accumulation
     assert np.abs(b.grad.cpu().numpy() - a.grad.numpy()).max() <= 5e-6, "case %d: gradient" % i
+
+
+def test_the_references_own_test_file_passes_over_the_dropins(cuda_device):
+  """test/test_training_utils.py of the reference, UNMODIFIED and executed by file path from baseline/_ref/: its
+  `from kinematics.penalties import ...` (line 4) resolves to this repo's drop-in, so its two known-answer tests run on
+  libikl.so (CPU tensors in and out, as the reference's tests pass them; the launch counter proves the kernels ran)."""
+  import importlib.util
+  import inspect
+  import os
+  from conftest import PKG, reference_root
+  from ikl import _cabi
+  root = reference_root()
+  if root is None:
+    pytest.skip("no copy of the reference (baseline/_ref or /root/reference)")
+  path = os.path.join(root, "test", "test_training_utils.py")
+  spec = importlib.util.spec_from_file_location("_ref_test_training_utils", path)
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  src = os.path.realpath(inspect.getsourcefile(mod.piecewise_circle_penalty))
+  assert src.startswith(os.path.realpath(PKG) + os.sep), "the reference's test must be exercising the drop-in, not %s" % src
+  tests = [(n, f) for n, f in sorted(vars(mod).items()) if n.startswith("test_") and callable(f)]
+  assert [n for n, _ in tests] == ["test_piecewise_circle_penalty", "test_piecewise_joint_limit_penalty"]
+  before = _cabi.launch_count()
+  for _, fn in tests:
+    fn()
+  assert _cabi.launch_count() - before >= 2, "at least one libikl.so launch per penalty call"
