@@ -20,6 +20,9 @@ PARITY PINNING (see tests/test_oracle_pinned.py and tests/golden/):
     its outputs (fp32 + fp64) as fixtures; this oracle must reproduce them bit-for-bit
     in fp32 for per-sample values and to fp32 round-off for batch sums;
   * the shipped multipliers.pth sizes (1/4/7/16/16) pin the constraint layout.
+  * tests/test_oracle_vs_live_reference.py executes the reference's own forward_kinematics.py / penalties.py by file
+    path (baseline/_ref or /root/reference) on derandomised hypothesis-drawn inputs -- shapes, slopes in either
+    order, reversed limits, exact kinks -- and requires bit equality of values and gradients in fp32 and fp64.
 
 The closed-form gradient (``lagrangian_grad_closed_form``) is an independent derivation
  evaluated in numpy fp64; it cross-checks both torch autograd on
